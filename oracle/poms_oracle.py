@@ -1,0 +1,513 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY -- CPU restatement of the POMS multigrid solve path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product (poms_b200/) never does: it has no CPU fallback.
+
+Parity status: PINNED.  tests/test_oracle_golden.py checks every function below against
+tests/golden/*.npz, which oracle/gen_golden.py produced by running the UNMODIFIED reference
+modules (over the serial spl stand-in in oracle/shim/) on the reference's own fixtures.
+Third-party arithmetic that is absent from /root/reference (package `spl`, unpinned,
+requirements.txt:4) is restated from its published definitions: clamped uniform knot
+vectors, Boehm knot insertion, Gauss-Legendre B-spline mass/stiffness.  3-D has no
+reference implementation except the banded Kronecker solve
+(pyccel/pyccel_functions.py:174-248); 3-D operators here are the dimension-generic form
+of the 2-D reference and are marked EXTENSION.
+
+Every vector is a NumPy fp64 array of shape (n1, ..., nd), C order, axis 1 slowest
+(sources/mg_jac.py:106-108).  A 1-D banded matrix is an (n, 2p+1) array `band` with
+band[i, k] = A[i, i+k-p] (column k <-> diagonal offset k-p; pyccel/pyccel_functions.py:15,19),
+entries that fall outside the matrix are zero (`remove_spurious_entries`).
+"""
+from math import sqrt
+
+import numpy as np
+from scipy.linalg.lapack import dgbtrf, dgbtrs, dgetrf, dgetrs
+
+# =============================================================================================
+# 1-D spline setup (what `spl` provides to sources/mg_jac.py:27-46,67 and matrix_assembler.py)
+# =============================================================================================
+
+
+def make_open_knots(p, n):
+    """Clamped uniform knots, n basis functions (sources/mg_jac.py:28-29 call sites)."""
+    N = n - p
+    T = np.zeros(n + p + 1)
+    T[p + 1:n] = np.arange(1, N) / N
+    T[n:] = 1.0
+    return T
+
+
+def knots_to_insert(Tf, nf, pf, Tc, nc, pc):
+    """sources/multilevels.py:7-33: interior fine knots Tf[pf+1..nf-1] that are not bit-equal
+    to any interior coarse knot Tc[pc+1..nc]."""
+    out = []
+    for i in range(pf + 1, nf):
+        t = Tf[i]
+        j = pc + 1
+        found = False
+        while True:
+            if t < Tc[j]:
+                break
+            if t == Tc[j]:
+                found = True
+            j += 1
+            if j > nc:
+                break
+        # reference line 29: the while loop always ends with condition False, so the knot
+        # is kept iff it was never found
+        if not found:
+            out.append(t)
+    return np.array(out)
+
+
+def fine_knots(Tc, ts):
+    """sources/mg_jac.py:32-35: sorted union of the coarse knots and the inserted ones."""
+    return np.sort(np.concatenate([np.asarray(Tc, float), np.asarray(ts, float)]), kind="stable")
+
+
+def insertion_matrix(ts, n, p, knots):
+    """`matrix_multi_stages(ts, n, p, knots)` (sources/mg_jac.py:67): product of single-knot
+    Boehm insertion matrices; (n+len(ts)) x n, maps coarse to fine coefficients."""
+    T = np.array(knots, dtype=float)
+    M = np.eye(n)
+    for t in ts:
+        m = len(T) - p - 1
+        k = int(np.searchsorted(T, t, side="right")) - 1
+        Q = np.zeros((m + 1, m))
+        for i in range(m + 1):
+            if i <= k - p:
+                a = 1.0
+            elif i <= k:
+                a = (t - T[i]) / (T[i + p] - T[i])
+            else:
+                a = 0.0
+            if i < m:
+                Q[i, i] += a
+            if i >= 1:
+                Q[i, i - 1] += 1.0 - a
+        M = Q @ M
+        T = np.concatenate([T[:k + 1], [t], T[k + 1:]])
+    return M
+
+
+def _basis_and_ders(T, p, span, x):
+    """Cox-de Boor values and first derivatives of the p+1 non-zero B-splines on
+    [T[span], T[span+1]) at points x.  Returns (p+1, len(x)) arrays."""
+    x = np.asarray(x, float)
+    N = np.zeros((p + 1, p + 1, len(x)))  # N[d][j]: degree d, j-th function
+    N[0, 0] = 1.0
+    for d in range(1, p + 1):
+        for j in range(d + 1):
+            i = span - d + j  # global index of the degree-d function
+            v = 0.0
+            if j >= 1:
+                den = T[i + d] - T[i]
+                if den > 0:
+                    v = v + (x - T[i]) / den * N[d - 1, j - 1]
+            if j <= d - 1:
+                den = T[i + d + 1] - T[i + 1]
+                if den > 0:
+                    v = v + (T[i + d + 1] - x) / den * N[d - 1, j]
+            N[d, j] = v
+    vals = N[p].copy()
+    ders = np.zeros_like(vals)
+    for j in range(p + 1):
+        i = span - p + j
+        if j >= 1:
+            den = T[i + p] - T[i]
+            if den > 0:
+                ders[j] += p / den * N[p - 1, j - 1]
+        if j <= p - 1:
+            den = T[i + p + 1] - T[i + 1]
+            if den > 0:
+                ders[j] -= p / den * N[p - 1, j]
+    return vals, ders
+
+
+def assemble_1d(p, T):
+    """1-D mass M and stiffness K (dense n x n) on knot vector T: the integrals that
+    sources/matrix_assembler.py:59-74 accumulate (v_m, v_s), Gauss-Legendre p+1 points/element."""
+    T = np.asarray(T, float)
+    n = len(T) - p - 1
+    u, w = np.polynomial.legendre.leggauss(p + 1)
+    M = np.zeros((n, n))
+    K = np.zeros((n, n))
+    for span in range(p, n):
+        a, b = T[span], T[span + 1]
+        if b <= a:
+            continue
+        x = 0.5 * (a + b) + 0.5 * (b - a) * u
+        wq = 0.5 * (b - a) * w
+        v, dv = _basis_and_ders(T, p, span, x)
+        i0 = span - p
+        M[i0:i0 + p + 1, i0:i0 + p + 1] += (v * wq) @ v.T
+        K[i0:i0 + p + 1, i0:i0 + p + 1] += (dv * wq) @ dv.T
+    return M, K
+
+
+def dense_to_band(A, p):
+    """(n, 2p+1) band of a dense matrix (what sources/utils.py:105-134 extracts)."""
+    n = A.shape[0]
+    band = np.zeros((n, 2 * p + 1))
+    for k in range(-p, p + 1):
+        i = np.arange(max(0, -k), min(n, n - k))
+        band[i, k + p] = A[i, i + k]
+    return band
+
+
+def band_to_dense(band):
+    n, w = band.shape
+    p = (w - 1) // 2
+    A = np.zeros((n, n))
+    for k in range(-p, p + 1):
+        i = np.arange(max(0, -k), min(n, n - k))
+        A[i, i + k] = band[i, k + p]
+    return A
+
+
+def glt_band(p, n, degree=None):
+    """Symmetric Toeplitz band t_k = phi_q((q+1)/2 + k) of the cardinal B-spline of degree
+    q (default q=p), stored with half-bandwidth p.  `collocation_cardinal_splines` itself is
+    UNPINNED (absent third-party code); M1, M2 are *inputs* of pcg_glt (solvers.py:239)."""
+    from scipy.interpolate import BSpline
+    q = p if degree is None else degree
+    b = BSpline.basis_element(np.arange(q + 2, dtype=float), extrapolate=False)
+    band = np.zeros((n, 2 * p + 1))
+    for k in range(-p, p + 1):
+        v = float(np.nan_to_num(b((q + 1) / 2.0 + k)))
+        i = np.arange(max(0, -k), min(n, n - k))
+        band[i, k + p] = v
+    return band
+
+
+# =============================================================================================
+# Operators
+# =============================================================================================
+
+
+def apply_band(band, X, axis):
+    """Y = A applied along `axis` of X (one stage of sources/kron_product.py:80-86)."""
+    n, w = band.shape
+    p = (w - 1) // 2
+    X = np.moveaxis(X, axis, 0)
+    assert X.shape[0] == n
+    Y = np.zeros_like(X)
+    bshape = (-1,) + (1,) * (X.ndim - 1)
+    for k in range(-p, p + 1):
+        lo, hi = max(0, -k), min(n, n - k)
+        if hi > lo:
+            Y[lo:hi] += band[lo:hi, k + p].reshape(bshape) * X[lo + k:hi + k]
+    return np.moveaxis(Y, 0, axis)
+
+
+def kron_dot(A, B, X):
+    """kron_dot_v2(A, B, X) = A X B^T (sources/kron_product.py:56-89): stage 1 contracts the
+    last axis with B, stage 2 the first axis with A."""
+    return apply_band(A, apply_band(B, X, 1), 0)
+
+
+class KronSumOperator:
+    """A = sum_t A_1^t (x) ... (x) A_d^t with banded 1-D factors.  For the reference weak form
+    -Lap(u)+u (sources/matrix_assembler.py:82-83,173) the full 2-D StencilMatrix equals
+    K(x)M + M(x)(K+M); 3-D (EXTENSION): K(x)M(x)M + M(x)K(x)M + M(x)M(x)(K+M)."""
+
+    def __init__(self, terms):
+        self.terms = [tuple(np.asarray(b, float) for b in t) for t in terms]
+        self.npts = tuple(b.shape[0] for b in self.terms[0])
+        self.pads = tuple((b.shape[1] - 1) // 2 for b in self.terms[0])
+        self.ndim = len(self.npts)
+        n = int(np.prod(self.npts))
+        self.shape = (n, n)
+
+    def dot(self, X):
+        Y = np.zeros_like(X)
+        for t in self.terms:
+            Z = X
+            for ax in range(self.ndim - 1, -1, -1):
+                Z = apply_band(t[ax], Z, ax)
+            Y += Z
+        return Y
+
+    def diagonal(self):
+        D = np.zeros(self.npts)
+        for t in self.terms:
+            d = np.ones(())
+            for b, p in zip(t, self.pads):
+                d = np.multiply.outer(d, b[:, p])
+            D += d
+        return D
+
+    def to_stencil(self):
+        """Full (n1,n2,2p1+1,2p2+1) stencil array of the 2-D operator (spl StencilMatrix)."""
+        assert self.ndim == 2
+        S = 0.0
+        for a, b in self.terms:
+            S = S + a[:, None, :, None] * b[None, :, None, :]
+        return S
+
+    def tocsr(self):
+        from scipy.sparse import kron, csr_matrix
+        out = None
+        for t in self.terms:
+            m = csr_matrix(band_to_dense(t[0]))
+            for b in t[1:]:
+                m = kron(m, csr_matrix(band_to_dense(b)), format="csr")
+            out = m if out is None else out + m
+        return out.tocsr()
+
+
+class StencilOperator2D:
+    """The reference's full 2-D StencilMatrix (a3): v[i1,i2] = sum M[i1,i2,k1,k2] u[i1+k1,i2+k2]
+    (slides/content.tex:285-290); data as stored by the shim, (n1, n2, 2p1+1, 2p2+1)."""
+
+    def __init__(self, data):
+        self.data = np.asarray(data, float)
+        n1, n2, w1, w2 = self.data.shape
+        self.npts = (n1, n2)
+        self.pads = ((w1 - 1) // 2, (w2 - 1) // 2)
+        self.shape = (n1 * n2, n1 * n2)
+
+    def dot(self, X):
+        n1, n2 = self.npts
+        p1, p2 = self.pads
+        Xp = np.zeros((n1 + 2 * p1, n2 + 2 * p2))
+        Xp[p1:p1 + n1, p2:p2 + n2] = X
+        Y = np.zeros((n1, n2))
+        for k1 in range(2 * p1 + 1):
+            for k2 in range(2 * p2 + 1):
+                Y += self.data[:, :, k1, k2] * Xp[k1:k1 + n1, k2:k2 + n2]
+        return Y
+
+    def diagonal(self):
+        return self.data[:, :, self.pads[0], self.pads[1]].copy()
+
+
+def poisson_operator(p, knots_per_axis):
+    """-Lap(u)+u on a tensor-product spline space as a Kronecker sum (see KronSumOperator)."""
+    MK = [assemble_1d(p, T) for T in knots_per_axis]
+    Mb = [dense_to_band(M, p) for M, K in MK]
+    Kb = [dense_to_band(K, p) for M, K in MK]
+    d = len(MK)
+    terms = []
+    for a in range(d):
+        t = []
+        for b in range(d):
+            if b == a:
+                t.append(Kb[b] + Mb[b] if a == d - 1 else Kb[b])
+            else:
+                t.append(Mb[b])
+        terms.append(tuple(t))
+    return KronSumOperator(terms), Mb, Kb
+
+
+# =============================================================================================
+# Kronecker solves (sources/kron_product.py:93-239, pyccel/pyccel_functions.py:114-248)
+# =============================================================================================
+
+
+def to_bnd(A):
+    """LAPACK general-band storage (sources/tests/test_kron_solve_bnd.py:30-42; the copy in
+    sources/kron_product.py:175-187 raises NameError): A_bnd[la+ua+i-j, j] = A[i, j]."""
+    n = A.shape[0]
+    nz = np.nonzero(A)
+    la = int(max(0, (nz[0] - nz[1]).max()))
+    ua = int(max(0, (nz[1] - nz[0]).max()))
+    A_bnd = np.zeros((1 + ua + 2 * la, n))
+    i, j = nz
+    A_bnd[la + ua + i - j, j] = A[i, j]
+    return A_bnd, la, ua
+
+
+def kron_solve_dense(mats, Y):
+    """kron_solve_serial / kron_solve_par (sources/kron_product.py:93-170): dense dgetrf of each
+    factor, then per-axis dgetrs sweeps, axis 1 first."""
+    X = np.array(Y, dtype=float)
+    for ax, A in enumerate(mats):
+        lu, piv, info = dgetrf(A)
+        Z = np.moveaxis(X, ax, 0)
+        shp = Z.shape
+        sol, info = dgetrs(lu, piv, np.ascontiguousarray(Z.reshape(shp[0], -1)))
+        X = np.moveaxis(sol.reshape(shp), 0, ax)
+    return np.ascontiguousarray(X)
+
+
+def kron_solve_banded(factors, Y):
+    """kron_solve_bnd_par (sources/kron_product.py:191-239) and its 3-D analogue
+    (pyccel/pyccel_functions.py:174-248): `factors[a] = (lu_band, la, ua, piv)` as returned by
+    dgbtrf; dgbtrs along axis 1, then 2, then 3."""
+    X = np.array(Y, dtype=float)
+    for ax, (lub, la, ua, piv) in enumerate(factors):
+        Z = np.moveaxis(X, ax, 0)
+        shp = Z.shape
+        sol, info = dgbtrs(lub, la, ua, np.ascontiguousarray(Z.reshape(shp[0], -1)), piv)
+        X = np.moveaxis(sol.reshape(shp), 0, ax)
+    return np.ascontiguousarray(X)
+
+
+def band_factor(band):
+    """dgbtrf of a (n, 2p+1) band matrix -> (lu_band, la, ua, piv) with la = ua = p."""
+    n, w = band.shape
+    p = (w - 1) // 2
+    ab = np.zeros((3 * p + 1, n))
+    for k in range(-p, p + 1):
+        i = np.arange(max(0, -k), min(n, n - k))
+        ab[2 * p - k, i + k] = band[i, k + p]
+    lub, piv, info = dgbtrf(ab, p, p)
+    assert info == 0
+    return lub, p, p, piv
+
+
+# =============================================================================================
+# Iterative solvers: verbatim operation order of sources/solvers.py
+# =============================================================================================
+
+
+def _dot(a, b, log):
+    v = float(np.dot(a.ravel(), b.ravel()))
+    if log is not None:
+        log.append(v)
+    return v
+
+
+def jacobi(A, b, log=None):
+    """sources/solvers.py:139-163: x = b / diag(A)."""
+    return b / A.diagonal()
+
+
+def damped_jacobi(A, b, x0=None, tol=1e-6, maxiter=10, log=None):
+    """sources/solvers.py:167-235.  omega = 2/3 (193); dr = omega*r/diag (213); x = x + dr
+    (217); early exit when dr.dr < tol**2, tested AFTER the update (219-222); returns x only."""
+    omega = 2.0 / 3
+    D = A.diagonal()
+    x = 0.0 * b.copy() if x0 is None else x0.copy()
+    tol_sqr = tol ** 2
+    for k in range(1, maxiter + 1):
+        r = b - A.dot(x)
+        dr = omega * r / D
+        x = x + dr
+        nrmr = _dot(dr, dr, log)
+        if nrmr < tol_sqr:
+            break
+    return x
+
+
+def pcg(A, psolve, b, x0=None, tol=1e-6, maxiter=100, log=None):
+    """sources/solvers.py:69-135, including its quirks: stopping rule
+    r.r < tol*sqrt(r0.r0) (87,111-113); niter decremented on break (114); the discarded
+    mat-vec of line 109 has no observable effect and is omitted."""
+    x = 0.0 * b.copy() if x0 is None else x0.copy()
+    r = b - A.dot(x)
+    nrmr0 = sqrt(_dot(r, r, log))
+    s = psolve(A, r)
+    p = s
+    sr = _dot(s, r, log)
+    hist = []
+    k = 0
+    nrmr = nrmr0 ** 2
+    for k in range(1, maxiter + 1):
+        q = A.dot(p)
+        alpha = sr / _dot(p, q, log)
+        x = x + alpha * p
+        r = r - alpha * q
+        nrmr = _dot(r, r, log)
+        hist.append(nrmr)
+        if nrmr < tol * nrmr0:
+            k -= 1
+            break
+        s = psolve(A, r)
+        srold = sr
+        sr = _dot(s, r, log)
+        beta = sr / srold
+        p = s + beta * p
+    info = {"niter": k, "success": nrmr < tol * nrmr0, "res_norm": sqrt(nrmr),
+            "history": np.sqrt(np.array(hist))}
+    return x, info
+
+
+def pcg_glt(A, M1, M2, b, x0=None, tol=1e-6, maxiter=100, log=None, factors=None):
+    """sources/solvers.py:239-306: pcg whose preconditioner is kron_solve_par(M2, M1, r)
+    (260, 288): the FIRST argument acts along axis 1.  M1, M2 are (n, 2p+1) bands."""
+    mats = [band_to_dense(M2), band_to_dense(M1)]
+
+    def psolve(A_, r):
+        return kron_solve_dense(mats, r)
+
+    return pcg(A, psolve, b, x0=x0, tol=tol, maxiter=maxiter, log=log)
+
+
+def crl(A, b, x0=None, tol=1e-5, maxiter=1000, log=None):
+    """sources/solvers.py:3-65 (conjugate residuals)."""
+    x = 0.0 * b.copy() if x0 is None else x0.copy()
+    r = b - A.dot(x)
+    p = r.copy()
+    q = A.dot(p)
+    s = q.copy()
+    sr = _dot(s, r, log)
+    tol_sqr = tol ** 2
+    k = 0
+    for k in range(1, maxiter + 1):
+        if sr < tol_sqr:
+            k -= 1
+            break
+        alpha = sr / _dot(q, q, log)
+        x = x + alpha * p
+        r = r - alpha * q
+        s = A.dot(r)
+        srold = sr
+        sr = _dot(s, r, log)
+        beta = sr / srold
+        p = r + beta * p
+        q = s + beta * q
+    info = {"niter": k, "success": sr < tol_sqr, "res_norm": sqrt(sr)}
+    return x, info
+
+
+# =============================================================================================
+# Grid transfer and the two-grid cycle (sources/mg_jac.py, sources/mg_glt.py)
+# =============================================================================================
+
+
+def restrict(P1s, R):
+    """rc = (P1^T (x) ... (x) P1^T) rf  (sources/mg_jac.py:68-69,94), applied axis by axis."""
+    for ax, P1 in enumerate(P1s):
+        R = np.moveaxis(np.tensordot(P1.T, R, axes=([1], [ax])), 0, ax)
+    return R
+
+
+def prolong(P1s, E):
+    """ef = (P1 (x) ... (x) P1) ec  (sources/mg_jac.py:70,102)."""
+    for ax, P1 in enumerate(P1s):
+        E = np.moveaxis(np.tensordot(P1, E, axes=([1], [ax])), 0, ax)
+    return E
+
+
+def galerkin_dense(A_csr, P1s):
+    """Ac = R * Af * P (sources/mg_jac.py:81), dense result."""
+    from scipy.sparse import kron, csr_matrix
+    P = csr_matrix(P1s[0])
+    for P1 in P1s[1:]:
+        P = kron(P, csr_matrix(P1), format="csr")
+    return (P.T @ A_csr @ P).toarray()
+
+
+def two_grid(A, P1s, Ac_dense, b, post="jac", M1=None, M2=None, p=None, log_pre=None,
+             log_post=None):
+    """One two-grid cycle exactly as sources/mg_jac.py:85-119 (post='jac') or
+    sources/mg_glt.py:84-123 (post='glt'): PCG-Jacobi pre-smoothing (tol 1e-6, 10 its),
+    residual, restriction, direct coarse solve (splu, 98-99), prolongation + correction,
+    post-smoothing (PCG-Jacobi 10 its, or pcg_glt p+1 its)."""
+    from scipy.sparse import csc_matrix
+    from scipy.sparse.linalg import splu
+    out = {}
+    xf, info_pre = pcg(A, damped_jacobi, b, tol=1e-6, maxiter=10, log=log_pre)
+    rf = b - A.dot(xf)
+    rc = restrict(P1s, rf)
+    xc = splu(csc_matrix(Ac_dense)).solve(rc.ravel()).reshape(rc.shape)
+    xf1 = xf + prolong(P1s, xc)
+    if post == "jac":
+        xf2, info_post = pcg(A, damped_jacobi, b, x0=xf1, tol=1e-6, maxiter=10, log=log_post)
+    else:
+        xf2, info_post = pcg_glt(A, M1, M2, b, x0=xf1, tol=1e-6, maxiter=p + 1, log=log_post)
+    out.update(x_pre=xf, info_pre=info_pre, r_f=rf, r_c=rc, x_c=xc, x_corr=xf1, x_post=xf2,
+               info_post=info_post)
+    return out

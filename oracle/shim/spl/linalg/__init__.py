@@ -1,0 +1,1 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY (spl stand-in)."""

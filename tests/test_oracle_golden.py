@@ -1,0 +1,223 @@
+"""Pins oracle/poms_oracle.py (the CPU restatement) against tests/golden/*.npz, i.e. against
+outputs of the UNMODIFIED reference modules (provenance: oracle/gen_golden.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import poms_oracle as po
+from conftest import GOLDEN
+
+RT = 1e-12
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("name", ["kron_dot_fixture", "kron_dot_random"])
+def test_kron_dot(golden, name):
+    g = golden(name)
+    Y = po.kron_dot(g["A"], g["B"], g["X"])
+    assert rel(Y, g["Y_v2"]) < 1e-14
+    assert rel(Y, g["Y_ref"]) < 1e-14
+    op = po.KronSumOperator([(g["A"], g["B"])])
+    assert rel(op.dot(g["X"]), g["Y_v2"]) < 1e-14
+
+
+@pytest.mark.parametrize("name", ["kron_solve_fixture", "kron_solve_random"])
+def test_kron_solve_dense(golden, name):
+    g = golden(name)
+    X = po.kron_solve_dense([po.band_to_dense(g["A"]), po.band_to_dense(g["B"])], g["Y"])
+    assert rel(X, g["X_serial"]) < RT
+    assert rel(X, g["X_par"]) < RT
+    assert rel(X, g["X_ref"]) < RT
+
+
+@pytest.mark.parametrize("name", ["sym64", "nonsym10", "nonsym_rect", "pivot"])
+def test_kron_solve_banded_2d(golden, name):
+    g = golden("kron_solve_bnd_" + name)
+    la1, ua1, la2, ua2 = g["lu"]
+    f = [(g["A1_lu"], la1, ua1, g["piv1"]), (g["A2_lu"], la2, ua2, g["piv2"])]
+    X = po.kron_solve_banded(f, g["Y"])
+    assert rel(X, g["X"]) < RT
+    assert rel(X, g["X_splu"]) < 1e-10
+    # our own factorisation path (band -> dgbtrf) reproduces the same solution
+    f2 = [po.band_factor(g["A1"]), po.band_factor(g["A2"])]
+    assert rel(po.kron_solve_banded(f2, g["Y"]), g["X"]) < RT
+    # to_bnd restatement
+    b1, la, ua = po.to_bnd(po.band_to_dense(g["A1"]))
+    assert (la, ua) == (la1, ua1) and np.array_equal(b1, g["A1_bnd"])
+
+
+@pytest.mark.parametrize("name", ["kron_solve_bnd3d_fixture", "kron_solve_bnd3d_nonsym",
+                                  "kron_solve_bnd2d_nonsym"])
+def test_kron_solve_banded_pyccel(golden, name):
+    g = golden(name)
+    keys = [k for k in ("A1", "A2", "A3") if k in g]
+    f = []
+    for k, (la, ua) in zip(keys, g["lu"]):
+        from scipy.linalg.lapack import dgbtrf
+        lub, piv, info = dgbtrf(g[k + "_bnd"], la, ua)
+        f.append((lub, la, ua, piv))
+    X = po.kron_solve_banded(f, g["Y"])
+    assert rel(X, g["X"]) < RT
+    if "X_dense" in g:
+        assert rel(X, g["X_dense"]) < 1e-11
+
+
+def test_knots_and_insertion(golden):
+    g = golden("knots_to_insert")
+    for i in range(int(g["ncases"])):
+        pf, nf, pc, nc = g["case%d_params" % i]
+        Tc = po.make_open_knots(pc, nc)
+        Tf = po.make_open_knots(pf, nf)
+        assert np.array_equal(Tc, g["case%d_Tc" % i])
+        assert np.array_equal(Tf, g["case%d_Tf" % i])
+        ts = po.knots_to_insert(Tf, nf, pf, Tc, nc, pc)
+        assert np.array_equal(ts, g["case%d_ts" % i])
+        P1 = g["case%d_P1" % i]
+        if P1.size:
+            assert rel(po.insertion_matrix(ts, nc, pc, Tc), P1) < 1e-14
+
+
+def test_insertion_matrix_is_spline_identity():
+    # independent pin of `matrix_multi_stages`: coarse spline == refined spline pointwise
+    from scipy.interpolate import BSpline
+    p, nc, nf = 3, 11, 19
+    Tc, Tf = po.make_open_knots(p, nc), po.make_open_knots(p, nf)
+    ts = po.knots_to_insert(Tf, nf, p, Tc, nc, p)
+    T = po.fine_knots(Tc, ts)
+    assert np.array_equal(T, Tf)
+    P1 = po.insertion_matrix(ts, nc, p, Tc)
+    c = np.random.default_rng(0).standard_normal(nc)
+    x = np.linspace(0, 1, 101)[:-1]
+    assert np.abs(BSpline(Tc, c, p)(x) - BSpline(T, P1 @ c, p)(x)).max() < 1e-13
+
+
+def test_assembly_1d_mass(golden):
+    g = golden("assembly_1d")
+    for key in g.files:
+        p, ne = int(key.split("_")[1][1:]), int(key.split("_")[2][2:])
+        T = po.make_open_knots(p, ne + p)
+        M, K = po.assemble_1d(p, T)
+        assert rel(po.dense_to_band(M, p), g[key]) < 1e-13
+        assert abs(K.sum()) < 1e-10 and abs(M.sum() - 1.0) < 1e-13
+
+
+def _problem(g):
+    p, ne = int(g["p"]), int(g["ne"])
+    T = po.make_open_knots(p, ne + p)
+    A, Mb, Kb = po.poisson_operator(p, [T, T])
+    return A, po.StencilOperator2D(g["A"])
+
+
+@pytest.mark.parametrize("tag", ["p1_ne16", "p2_ne10", "p3_ne12"])
+def test_kron_sum_equals_reference_assembly(golden, tag):
+    # the Kronecker-sum operator IS the reference's assembled 2-D StencilMatrix (a3)
+    g = golden("pcg_jacobi_" + tag)
+    A, S = _problem(g)
+    assert rel(A.to_stencil(), g["A"]) < 1e-12
+    X = np.random.default_rng(1).standard_normal(A.npts)
+    assert rel(A.dot(X), S.dot(X)) < 1e-12
+    assert rel(A.diagonal(), S.diagonal()) < 1e-13
+    assert rel(A.tocsr() @ X.ravel(), S.dot(X).ravel()) < 1e-12
+
+
+def _check_dots(mine, ref, rtol=1e-8):
+    mine, ref = np.array(mine), np.array(ref)
+    assert len(mine) == len(ref), (len(mine), len(ref))
+    assert np.allclose(mine, ref, rtol=rtol, atol=1e-30)
+
+
+@pytest.mark.parametrize("tag", ["p1_ne16", "p2_ne10", "p3_ne12"])
+@pytest.mark.parametrize("opkind", ["stencil", "kronsum"])
+def test_pcg_damped_jacobi(golden, tag, opkind):
+    g = golden("pcg_jacobi_" + tag)
+    A, S = _problem(g)
+    op = S if opkind == "stencil" else A
+    log = []
+
+    def psolve(A_, r):
+        return po.damped_jacobi(A_, r, log=log)
+
+    x, info = po.pcg(op, psolve, g["b"], tol=float(g["tol"]), maxiter=int(g["maxiter"]), log=log)
+    assert info["niter"] == int(g["info"][0])
+    assert info["success"] == bool(g["info"][1])
+    assert abs(info["res_norm"] - g["info"][2]) <= 1e-8 * g["info"][2]
+    assert rel(x, g["x"]) < 1e-10
+    _check_dots(log, g["dots"])
+
+
+@pytest.mark.parametrize("tag", ["p1_ne16", "p2_ne10", "p3_ne12"])
+def test_pcg_diag_jacobi_crl(golden, tag):
+    g = golden("pcg_diag_" + tag)
+    A, S = _problem(g)
+    log = []
+    x, info = po.pcg(S, po.jacobi, g["b"], tol=float(g["tol"]), maxiter=int(g["maxiter"]), log=log)
+    assert info["niter"] == int(g["info"][0]) and rel(x, g["x"]) < 1e-10
+    _check_dots(log, g["dots"])
+    j = golden("jacobi_" + tag)
+    assert rel(po.jacobi(S, j["b"]), j["x_jacobi"]) < 1e-14
+    log = []
+    assert rel(po.damped_jacobi(S, j["b"], log=log), j["x_damped"]) < 1e-12
+    _check_dots(log, j["dots_damped"])
+    log = []
+    x2 = po.damped_jacobi(S, j["b"], x0=j["x_jacobi"], tol=1e-3, maxiter=25, log=log)
+    assert rel(x2, j["x_damped2"]) < 1e-12
+    _check_dots(log, j["dots_damped2"])
+    c = golden("crl_" + tag)
+    log = []
+    x, info = po.crl(A, c["b"], tol=1e-5, maxiter=60, log=log)
+    assert info["niter"] == int(c["info"][0]) and rel(x, c["x"]) < 1e-9
+    _check_dots(log, c["dots"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["p1_ne4", "p1_ne16", "p2_ne10", "p3_ne12"])
+def test_pcg_glt(golden, tag):
+    g = golden("pcg_glt_" + tag)
+    A, S = _problem(g)
+    log = []
+    x, info = po.pcg_glt(S, g["M1"], g["M2"], g["b"], tol=float(g["tol"]), maxiter=100, log=log)
+    assert info["niter"] == int(g["info"][0])
+    assert rel(x, g["x"]) < 1e-9
+    _check_dots(log, g["dots"], rtol=1e-6)
+    p = int(g["p"])
+    assert rel(po.glt_band(p, g["M1"].shape[0]), g["M1"]) < 1e-15
+
+
+@pytest.mark.parametrize("name", sorted(os.path.basename(f)[:-4] for f in
+                                        glob.glob(os.path.join(GOLDEN, "mg_*.npz"))))
+def test_two_grid(golden, name):
+    g = golden(name)
+    p, nf, nc = int(g["p"]), int(g["nf"]), int(g["nc"])
+    Tc, Tf = po.make_open_knots(p, nc), po.make_open_knots(p, nf)
+    ts = po.knots_to_insert(Tf, nf, p, Tc, nc, p)
+    assert np.array_equal(ts, g["Ts"])
+    T = po.fine_knots(Tc, ts)
+    assert np.array_equal(T, g["T"])
+    A, Mb, Kb = po.poisson_operator(p, [T, T])
+    assert tuple(g["n"]) == A.npts
+    assert rel(A.to_stencil(), g["A"]) < 1e-11
+    P1 = po.insertion_matrix(ts, nc, p, Tc)
+    assert rel(P1, g["P1"]) < 1e-14
+    Ac = po.galerkin_dense(A.tocsr(), [P1, P1])
+    assert rel(Ac, g["Ac"]) < 1e-11
+    # nested spaces: the Galerkin operator is the coarse-space assembled operator
+    Acoarse, _, _ = po.poisson_operator(p, [Tc, Tc])
+    assert rel(Acoarse.tocsr().toarray(), g["Ac"]) < 1e-10
+    b = np.ones(A.npts)
+    post = "glt" if name.startswith("mg_glt") else "jac"
+    lp, lq = [], []
+    kw = dict(M1=g["M1"], M2=g["M2"], p=p) if post == "glt" else {}
+    out = po.two_grid(A, [P1, P1], Ac, b, post=post, log_pre=lp, log_post=lq, **kw)
+    assert out["info_pre"]["niter"] == int(g["info_pre"][0])
+    assert out["info_post"]["niter"] == int(g["info_post"][0])
+    assert out["info_post"]["success"] == bool(g["info_post"][1])
+    for k in ("x_pre", "r_f", "x_corr", "x_post"):
+        assert rel(out[k], g[k]) < 1e-9, k
+    assert rel(out["r_c"].ravel(), g["r_c"]) < 1e-9
+    assert rel(out["x_c"].ravel(), g["x_c"]) < 1e-9
+    _check_dots(lp, g["dots_pre"], rtol=1e-6)
+    _check_dots(lq, g["dots_post"], rtol=1e-5)
