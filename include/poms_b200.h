@@ -1,0 +1,142 @@
+/*
+ * poms_b200.h -- C ABI of libpoms_b200.so: hand-written sm_100a fp64 kernels for the POMS
+ * multigrid solve path (tensor-product B-spline discretisations).
+ *
+ * The reference (pyccel/poms) is pure Python and has no FFI; its hot-path "interface" is a
+ * set of Python functions over `spl` stencil objects.  Each entry point below replaces the
+ * arithmetic of one of them; the Python package poms_b200/ keeps the reference names and
+ * signatures and binds these symbols with ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer (tensor.data_ptr()); no torch types cross this ABI;
+ *  - vectors are fp64, C order, axis 1 slowest (sources/mg_jac.py:106-108).  A d-dim vector
+ *    is described by its owned extent (n1[,n2],n3), the row pitch `ld` and the plane pitch
+ *    `pld` in doubles, and `glo`/`ghi` = number of readable ghost planes stored directly
+ *    below / above the owned planes along axis 1 (slab partition; 0 on one GPU);
+ *  - a 1-D banded matrix is an (n, 2p+1) row-major array, band[i][k] = A[i, i+k-p]
+ *    (pyccel/pyccel_functions.py:15,19); out-of-matrix entries must be zero;
+ *  - all launches go to the caller's `stream` (cudaStream_t cast to void*); nothing
+ *    allocates or synchronises; `ws` is a caller-owned workspace of poms_workspace_bytes()
+ *    bytes, zero-initialised once, private to one stream;
+ *  - return value: 0 ok, <0 = -(index of the bad argument), >0 = cudaError_t.
+ */
+#ifndef POMS_B200_H
+#define POMS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int poms_version(void);
+int64_t poms_workspace_bytes(void);
+const char* poms_last_error(void);
+/* number of kernel launches issued through this library since load (bench "gpu_launches") */
+int64_t poms_launch_count(void);
+
+/* operator forms for poms_kron_matvec_* */
+#define POMS_FORM_SINGLE 0 /* Y = (A1 (x) A2 [(x) A3]) X; the A's are passed in the m* slots   */
+#define POMS_FORM_SUM    1 /* Y = sum_a (M (x)..(x) K_a (x)..(x) M) X, separable elliptic form */
+/* epilogues: v = (A x)[i] */
+#define POMS_EPI_STORE  0  /* y = v                      ; dot += x*v   (p.q of CG)          */
+#define POMS_EPI_RESID  1  /* y = b - v                  ; dot += y*y   (r.r)                */
+#define POMS_EPI_JACOBI 2  /* y = x + om*(b - v)/diag(A) ; dot += dr*dr (damped Jacobi sweep) */
+#define POMS_EPI_DINV   3  /* y = om*(b - v)/diag(A)     ; dot += y*y   (Jacobi-preconditioned residual) */
+
+/*
+ * Kronecker-structured banded mat-vec, one fused pass (16 B/DOF algorithmic).
+ * Replaces: kron_dot_v2 / kron_dot_v1 (sources/kron_product.py:56-89, 10-52),
+ *           kron_dot_pyccel_2d (pyccel/pyccel_functions.py:4-21),
+ *           StencilMatrix.dot as used by the solvers (sources/solvers.py:85,103,209,256,274),
+ *           and, with POMS_EPI_JACOBI, the sweep of damped_jacobi (sources/solvers.py:209-219).
+ * All bands have the same half-bandwidth p (narrower ones are zero-padded by the caller).
+ * FORM_SINGLE: m1,m2[,m3] are the factors, k* ignored.  FORM_SUM: k of the LAST axis must
+ * already contain K+M (the "+u" term of sources/matrix_assembler.py:82-83).
+ * dot_out (may be NULL = no reduction): the fused reduction OVERWRITES *dot_out.
+ */
+int poms_kron_matvec_2d(const double* x, double* y, const double* b,
+                        int n1, int n2, int64_t ld, int glo, int ghi, int p, int form,
+                        const double* m1, const double* k1, const double* m2, const double* k2,
+                        int epilogue, double omega, double* dot_out, void* ws, void* stream);
+int poms_kron_matvec_3d(const double* x, double* y, const double* b,
+                        int n1, int n2, int n3, int64_t ld, int64_t pld, int glo, int ghi,
+                        int p, int form,
+                        const double* m1, const double* k1, const double* m2, const double* k2,
+                        const double* m3, const double* k3,
+                        int epilogue, double omega, double* dot_out, void* ws, void* stream);
+
+/*
+ * Full (non-separable) 2-D stencil mat-vec: y[i1,i2] = sum_{k1,k2} S[i1,i2,k1,k2] x[i1+k1-p1,i2+k2-p2]
+ * = spl StencilMatrix.dot (slides/content.tex:285-290; sources/solvers.py:85).  S is
+ * (n1, n2, 2p1+1, 2p2+1) row-major.  Same epilogues; diag = S[i1,i2,p1,p2].
+ */
+int poms_stencil_matvec_2d(const double* x, double* y, const double* b, const double* S,
+                           int n1, int n2, int64_t ld, int glo, int ghi, int p1, int p2,
+                           int epilogue, double omega, double* dot_out, void* ws, void* stream);
+
+/*
+ * BLAS-1 pieces of the CG drivers over a flat range of `n` doubles (the owned planes are
+ * contiguous because axis 1 is slowest).  Scalars live on the device: alpha = *num / *den.
+ */
+/* x += a p ; r -= a q ; *rr = r.r      (sources/solvers.py:104-111; 48 B/DOF)            */
+int poms_cg_update(double* x, double* r, const double* p, const double* q, int64_t n,
+                   const double* num, const double* den, double* rr_out, void* ws, void* stream);
+/* p = s + (num/den) p                  (sources/solvers.py:120-124)                         */
+int poms_p_update(double* p, const double* s, int64_t n, const double* num, const double* den,
+                  void* stream);
+/* *out = x.y                           (StencilVector.dot, local part)                      */
+int poms_dot(const double* x, const double* y, int64_t n, double* out, void* ws, void* stream);
+/* z = a x + b y  (y may be NULL -> z = a x); a, b host scalars                              */
+int poms_axpby(double* z, double a, const double* x, double b, const double* y, int64_t n,
+               void* stream);
+/* y += (num/den) * x with device scalars (crl: sources/solvers.py:44-54)                    */
+int poms_axpy_dev(double* y, const double* x, int64_t n, const double* num, const double* den,
+                  double sign, void* stream);
+/* x = om * b / diag(A) and *dot = x.x : first damped-Jacobi sweep from x0 = 0, and jacobi()
+ * with om = 1 (sources/solvers.py:139-163, 209-219).  diag from the Kronecker-sum bands. */
+int poms_jacobi_first_2d(double* x, const double* b, int n1, int n2, int64_t ld, int p, int form,
+                         const double* m1, const double* k1, const double* m2, const double* k2,
+                         double omega, double* dot_out, void* ws, void* stream);
+int poms_jacobi_first_3d(double* x, const double* b, int n1, int n2, int n3, int64_t ld,
+                         int64_t pld, int p, int form,
+                         const double* m1, const double* k1, const double* m2, const double* k2,
+                         const double* m3, const double* k3,
+                         double omega, double* dot_out, void* ws, void* stream);
+/* d = c1*d + c2*z ; x += d : one step of the Chebyshev smoother recurrence (40 B/DOF).
+ * EXTENSION (not in the reference): linear, symmetric form of the reference's PCG smoothers */
+int poms_cheb_update(double* x, double* d, const double* z, double c1, double c2, int64_t n,
+                     void* stream);
+/* x = om * b / d (d = explicit diagonal array, same layout), *dot = x.x                     */
+int poms_diag_scale(double* x, const double* b, const double* d, int64_t n, double omega,
+                    double* dot_out, void* ws, void* stream);
+
+/*
+ * Banded triangular solves of dgbtrs along one axis of a 2-D/3-D array, all lines at once.
+ * Replaces the per-line dgbtrs of kron_solve_bnd_par (sources/kron_product.py:226,232) and
+ * kron_solve_par_bnd_pyccel_{2d,3d} (pyccel/pyccel_functions.py:160,166,229-244).
+ * `ab` is the dgbtrf output in LAPACK band storage as a row-major (2kl+ku+1, n) array,
+ * `ipiv` the 0-based pivots (int32).  The array is viewed as (n_outer, n, n_inner) with
+ * strides (s_outer, s_axis, 1); y -> x (may alias).
+ */
+int poms_band_solve_axis(const double* y, double* x, const double* ab, const int32_t* ipiv,
+                         int n, int kl, int ku, int64_t n_outer, int64_t s_outer, int64_t s_axis,
+                         int64_t n_inner, void* stream);
+
+/*
+ * Per-axis sparse row-gather: out[o, i, c] (+)= sum_{w<W} coef[i*W+w] * in[o, start[i]+w, c].
+ * With the rows of P1 it is the prolongation, with the rows of P1^T the restriction of
+ * sources/mg_jac.py:67-70,94,102 applied one axis at a time (knot-insertion transfer).
+ * accumulate != 0 adds into out (prolong + correct, sources/mg_jac.py:112).
+ */
+int poms_axis_gather(const double* in, double* out, const int32_t* start, const double* coef,
+                     int W, int n_in, int n_out, int64_t n_outer, int64_t so_in, int64_t sa_in,
+                     int64_t so_out, int64_t sa_out, int64_t n_inner, int accumulate,
+                     void* stream);
+
+/* y = Ainv x, dense row-major n x n (replicated coarse direct solve, sources/mg_jac.py:98-99) */
+int poms_dense_matvec(const double* Ainv, const double* x, double* y, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -499,15 +499,140 @@ def two_grid(A, P1s, Ac_dense, b, post="jac", M1=None, M2=None, p=None, log_pre=
     from scipy.sparse import csc_matrix
     from scipy.sparse.linalg import splu
     out = {}
-    xf, info_pre = pcg(A, damped_jacobi, b, tol=1e-6, maxiter=10, log=log_pre)
+
+    def dj_pre(A_, r):
+        return damped_jacobi(A_, r, log=log_pre)
+
+    def dj_post(A_, r):
+        return damped_jacobi(A_, r, log=log_post)
+
+    xf, info_pre = pcg(A, dj_pre, b, tol=1e-6, maxiter=10, log=log_pre)
     rf = b - A.dot(xf)
     rc = restrict(P1s, rf)
     xc = splu(csc_matrix(Ac_dense)).solve(rc.ravel()).reshape(rc.shape)
     xf1 = xf + prolong(P1s, xc)
     if post == "jac":
-        xf2, info_post = pcg(A, damped_jacobi, b, x0=xf1, tol=1e-6, maxiter=10, log=log_post)
+        xf2, info_post = pcg(A, dj_post, b, x0=xf1, tol=1e-6, maxiter=10, log=log_post)
     else:
         xf2, info_post = pcg_glt(A, M1, M2, b, x0=xf1, tol=1e-6, maxiter=p + 1, log=log_post)
     out.update(x_pre=xf, info_pre=info_pre, r_f=rf, r_c=rc, x_c=xc, x_corr=xf1, x_post=xf2,
                info_post=info_post)
     return out
+
+
+# =============================================================================================
+# EXTENSION (no reference counterpart): multi-level V-cycle + MG-preconditioned CG.
+# Restates poms_b200/mg.py on the CPU with independent NumPy/SciPy building blocks so that the
+# GPU path can be checked for identical iteration counts and histories.  The outer driver is
+# the reference's pcg (above); only the stopping rule can be switched to the true relative one.
+# =============================================================================================
+
+
+def pcg_relative(A, psolve, b, x0=None, tol=1e-10, maxiter=200, log=None):
+    """pcg with the BASELINE metric's rule ||r|| <= tol*||r0|| instead of the reference's."""
+    x = 0.0 * b.copy() if x0 is None else x0.copy()
+    r = b - A.dot(x)
+    nrmr0 = sqrt(_dot(r, r, log))
+    thresh = (tol * nrmr0) ** 2
+    s = psolve(A, r)
+    p = s
+    sr = _dot(s, r, log)
+    hist = []
+    k = 0
+    nrmr = nrmr0 ** 2
+    for k in range(1, maxiter + 1):
+        q = A.dot(p)
+        alpha = sr / _dot(p, q, log)
+        x = x + alpha * p
+        r = r - alpha * q
+        nrmr = _dot(r, r, log)
+        hist.append(nrmr)
+        if nrmr <= thresh:
+            k -= 1
+            break
+        s = psolve(A, r)
+        srold = sr
+        sr = _dot(s, r, log)
+        p = s + (sr / srold) * p
+    return x, {"niter": k, "success": nrmr <= thresh, "res_norm": sqrt(nrmr),
+               "history": np.sqrt(np.array(hist)), "res_norm0": nrmr0}
+
+
+class MGHierarchy:
+    def __init__(self, p, N, Nc=8, smoother="glt", nu=1, ratio=4.0, safety=1.1):
+        from scipy.linalg import eigh
+        self.p, self.smoother, self.nu, self.ratio = p, smoother, nu, ratio
+        N = list(N)
+        d = len(N)
+        self.levels = []
+        while True:
+            knots = [make_open_knots(p, n + p) for n in N]
+            A, Mb, Kb = poisson_operator(p, knots)
+            self.levels.append(dict(N=list(N), knots=knots, A=A, Mb=Mb, Kb=Kb))
+            if all(n <= Nc for n in N):
+                break
+            nxt = [n // 2 if (n > Nc and n % 2 == 0) else n for n in N]
+            if nxt == N:
+                break
+            N = nxt
+        for f, c in zip(self.levels[:-1], self.levels[1:]):
+            P1s = []
+            for a in range(d):
+                nf, nc = f["N"][a] + p, c["N"][a] + p
+                if nf == nc:
+                    P1s.append(np.eye(nf))
+                    continue
+                ts = knots_to_insert(f["knots"][a], nf, p, c["knots"][a], nc, p)
+                P1s.append(insertion_matrix(ts, nc, p, c["knots"][a]))
+            f["P1s"] = P1s
+        self.Ainv_c = np.linalg.inv(self.levels[-1]["A"].tocsr().toarray())
+        for lv in self.levels[:-1]:
+            A = lv["A"]
+            if smoother == "glt":
+                q = max(2 * p - 1, 1)
+                bands = [glt_band(p, n, degree=q) for n in A.npts]
+                lv["glt"] = [band_factor(b) for b in bands]
+                muM = [eigh(band_to_dense(lv["Mb"][a]), band_to_dense(bands[a]),
+                            eigvals_only=True)[-1] for a in range(d)]
+                best = 0.0
+                for a in range(d):
+                    KM = band_to_dense(lv["Kb"][a]) + band_to_dense(lv["Mb"][a])
+                    muK = eigh(KM, band_to_dense(bands[a]), eigvals_only=True)[-1]
+                    best = max(best, muK * float(np.prod([muM[c] for c in range(d) if c != a])))
+                lv["lmax"] = safety * best
+            else:
+                raise NotImplementedError
+            lv["lmin"] = lv["lmax"] / ratio
+
+    def smooth(self, lv, b, x, zero_guess):
+        A = lv["A"]
+        theta = 0.5 * (lv["lmax"] + lv["lmin"])
+        delta = 0.5 * (lv["lmax"] - lv["lmin"])
+        sigma = theta / delta
+        rho = 1.0 / sigma
+        d = np.zeros_like(b)
+        for k in range(self.nu):
+            r = b if (k == 0 and zero_guess) else b - A.dot(x)
+            z = kron_solve_banded(lv["glt"], r)
+            if k == 0:
+                c1, c2 = 0.0, 1.0 / theta
+            else:
+                rho_n = 1.0 / (2.0 * sigma - rho)
+                c1, c2 = rho_n * rho, 2.0 * rho_n / delta
+                rho = rho_n
+            d = c1 * d + c2 * z
+            x = x + d
+        return x
+
+    def vcycle(self, l, b):
+        lv = self.levels[l]
+        if l == len(self.levels) - 1:
+            return (self.Ainv_c @ b.ravel()).reshape(b.shape)
+        x = self.smooth(lv, b, np.zeros_like(b), True)
+        r = b - lv["A"].dot(x)
+        x = x + prolong(lv["P1s"], self.vcycle(l + 1, restrict(lv["P1s"], r)))
+        return self.smooth(lv, b, x, False)
+
+    def mg_pcg(self, b, tol=1e-10, maxiter=200, log=None):
+        return pcg_relative(self.levels[0]["A"], lambda A_, r: self.vcycle(0, r), b, tol=tol,
+                            maxiter=maxiter, log=log)

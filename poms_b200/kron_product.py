@@ -1,0 +1,156 @@
+"""Drop-in for /root/reference/sources/kron_product.py (+ the raw-array variants of
+/root/reference/pyccel/kron_product.py): Kronecker mat-vec and Kronecker solves on the GPU.
+
+Same names, argument order and return values as the reference.  Dimension-generic
+extensions (`kron_dot`, `kron_solve_bnd`) take lists of factors.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import bsplines as bs
+from .stencil import (StencilVector, StencilMatrix, KronSumMatrix, DeviceContext, _stream)
+
+__all__ = ["kron_dot_v1", "kron_dot_v2", "kron_dot", "kron_solve_serial", "kron_solve_par",
+           "kron_solve_bnd_par", "kron_solve_bnd", "kron_solve_par_bnd_2d",
+           "kron_solve_par_bnd_3d", "to_bnd", "BandLU"]
+
+
+def _band_of(A):
+    return A._data if isinstance(A, StencilMatrix) else np.asarray(A, dtype=np.float64)
+
+
+def kron_dot(As, X):
+    """Y = (A_1 (x) ... (x) A_d) X for 1-D banded factors (d = 2, 3)."""
+    op = KronSumMatrix([_band_of(A) for A in As])
+    return op.dot(X)
+
+
+def kron_dot_v2(A, B, X):
+    """Y = (A kron B) X = A X B^T (/root/reference/sources/kron_product.py:56-89)."""
+    return kron_dot([A, B], X)
+
+
+def kron_dot_v1(A, B, X):
+    """Same result as kron_dot_v2 (/root/reference/sources/kron_product.py:10-52 computes it
+    entry by entry with ghost exchanges inside the loops)."""
+    return kron_dot([A, B], X)
+
+
+def to_bnd(A):
+    """1-D stencil matrix (or dense array) -> LAPACK general band storage (A_bnd, la, ua) with
+    A_bnd[la+ua+i-j, j] = A[i, j] (/root/reference/sources/kron_product.py:175-187, which
+    raises NameError there; working copy sources/tests/test_kron_solve_bnd.py:30-42)."""
+    D = A.toarray() if hasattr(A, "toarray") else np.asarray(A, dtype=float)
+    i, j = np.nonzero(D)
+    la = int(max(0, (i - j).max()))
+    ua = int(max(0, (j - i).max()))
+    A_bnd = np.zeros((1 + ua + 2 * la, D.shape[1]))
+    A_bnd[la + ua + i - j, j] = D[i, j]
+    return A_bnd, la, ua
+
+
+class BandLU:
+    """A dgbtrf factorisation resident on the device."""
+
+    def __init__(self, lub, kl, ku, piv, device):
+        self.n = lub.shape[1]
+        self.kl, self.ku = int(kl), int(ku)
+        if not (0 <= self.kl <= 5 and 0 <= self.ku <= 5):
+            raise ValueError("band solve supports kl, ku <= 5")
+        assert lub.shape[0] == 2 * self.kl + self.ku + 1
+        self.ab = torch.as_tensor(np.ascontiguousarray(lub, dtype=np.float64), device=device)
+        self.piv = torch.as_tensor(np.ascontiguousarray(piv, dtype=np.int32), device=device)
+
+    @classmethod
+    def from_band(cls, band, device):
+        return cls(*bs.band_lu(np.asarray(band, dtype=np.float64)), device)
+
+
+def _solve_axis(lu, src, dst, axis):
+    shape = tuple(src.space.local_shape)
+    n = shape[axis]
+    assert n == lu.n, "factor size does not match the axis"
+    n_outer = int(np.prod(shape[:axis])) if axis > 0 else 1
+    n_inner = int(np.prod(shape[axis + 1:])) if axis + 1 < len(shape) else 1
+    _lib.check(_lib.lib().poms_band_solve_axis(
+        src.ptr, dst.ptr, lu.ab.data_ptr(), lu.piv.data_ptr(), n, lu.kl, lu.ku, n_outer,
+        n * n_inner, n_inner, n_inner, _stream()), "poms_band_solve_axis")
+
+
+def kron_solve_bnd(factors, Y, X=None):
+    """X = (A_1 (x) .. (x) A_d)^-1 Y with pre-factored banded A_a (BandLU or the reference's
+    [A_bnd, la, ua, piv] lists); dgbtrs sweeps along axis 1, then 2 (, then 3) as in
+    /root/reference/pyccel/pyccel_functions.py:226-244."""
+    V = Y.space
+    if V.slab is not None and V.slab.size > 1:
+        from .dist import kron_solve_bnd_slab
+        return kron_solve_bnd_slab(factors, Y, X)
+    lus = [f if isinstance(f, BandLU) else BandLU(f[0], f[1], f[2], f[3], V.device)
+           for f in factors]
+    if X is None:
+        X = StencilVector(V)
+    src = Y
+    for ax, lu in enumerate(lus):
+        _solve_axis(lu, src, X, ax)
+        src = X
+    return X
+
+
+def kron_solve_bnd_par(A, B, Y):
+    """(X, elapsed) = solve (A kron B) X = Y with A = [A_bnd, la, ua, A_piv] as returned by
+    dgbtrf (/root/reference/sources/kron_product.py:191-239)."""
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    X = kron_solve_bnd([A, B], Y)
+    torch.cuda.synchronize()
+    return X, time.perf_counter() - t0
+
+
+def _cached_lu(A, device):
+    """dgbtrf of a 1-D StencilMatrix, cached on the object until its entries change."""
+    if not isinstance(A, StencilMatrix):
+        return BandLU.from_band(np.asarray(A, dtype=np.float64), device)
+    cache = A.__dict__.setdefault("_lu_cache", {})
+    key = str(device)
+    ent = cache.get(key)
+    if ent is None or not np.array_equal(ent[0], A._data):
+        cache[key] = (A._data.copy(), BandLU.from_band(A._data, device))
+    return cache[key][1]
+
+
+def kron_solve_serial(A, B, Y):
+    """X = (A kron B)^-1 Y (/root/reference/sources/kron_product.py:93-117).  The reference
+    densifies and dgetrf-factors both matrices on every call; here the banded factors are
+    computed once per matrix (dgbtrf) and the line solves run on the device."""
+    dev = Y.space.device
+    return kron_solve_bnd([_cached_lu(A, dev), _cached_lu(B, dev)], Y)
+
+
+def kron_solve_par(A, B, Y):
+    """MPI variant of kron_solve_serial (/root/reference/sources/kron_product.py:121-170): same
+    result; under a slab partition the axis-1 lines are solved after a slab<->pencil exchange
+    instead of one Allgatherv per line."""
+    return kron_solve_serial(A, B, Y)
+
+
+def kron_solve_par_bnd_2d(A_bnd, la, ua, B_bnd, lb, ub, Y, X, with_pycc=False):
+    """/root/reference/pyccel/kron_product.py:135-169: UNFACTORED LAPACK bands in, result
+    written into X (the pyccel kernel re-factorises on every call,
+    pyccel/pyccel_functions.py:146-147)."""
+    from scipy.linalg.lapack import dgbtrf
+    fa = dgbtrf(np.array(A_bnd, dtype=float), la, ua)
+    fb = dgbtrf(np.array(B_bnd, dtype=float), lb, ub)
+    return kron_solve_bnd([[fa[0], la, ua, fa[1]], [fb[0], lb, ub, fb[1]]], Y, X)
+
+
+def kron_solve_par_bnd_3d(A_bnd, la, ua, B_bnd, lb, ub, C_bnd, lc, uc, Y, X):
+    """/root/reference/pyccel/kron_product.py:171-192 (the only 3-D code of the reference)."""
+    from scipy.linalg.lapack import dgbtrf
+    fs = []
+    for ab, l, u in ((A_bnd, la, ua), (B_bnd, lb, ub), (C_bnd, lc, uc)):
+        f = dgbtrf(np.array(ab, dtype=float), l, u)
+        fs.append([f[0], l, u, f[1]])
+    return kron_solve_bnd(fs, Y, X)

@@ -1,0 +1,383 @@
+"""Grid transfer, two-grid cycle and the multi-level V-cycle / MG-preconditioned CG.
+
+Reference-faithful parts:
+  * `Transfer`: restriction r_c = (P1^T (x) P1^T) r_f and prolongation e_f = (P1 (x) P1) e_c of
+    /root/reference/sources/mg_jac.py:67-70,94,102, applied one axis at a time with
+    row-compressed knot-insertion matrices (never forming the Kronecker matrix);
+  * `CoarseSolver`: the replicated direct coarse solve of mg_jac.py:98-99.  The Galerkin operator
+    R*Af*P of a nested spline space is the coarse-space Kronecker sum, which is inverted exactly by
+    fast diagonalisation (dense 1-D generalised eigenbases, three small contractions);
+  * `two_grid`: one two-grid cycle in the exact order of mg_jac.py:85-119 / mg_glt.py:84-123.
+
+EXTENSION beyond the reference (labelled in every report):
+  * `Hierarchy`, `vcycle`, `mg_pcg`: recursive V-cycle used as the preconditioner of the
+    reference's own `pcg` driver.  Smoothers are the LINEAR, symmetric counterparts of the
+    reference's PCG smoothers -- a Chebyshev iteration preconditioned by damped-Jacobi's D^-1
+    ("jacobi") or by the GLT Kronecker solve T[m_{p-1}] (x) .. (x) T[m_{p-1}] ("glt",
+    /root/reference/slides/content.tex:141-153) -- because a fixed SPD preconditioner is what CG
+    needs (the reference's omega = 2/3 Jacobi diverges for p >= 3).
+"""
+from math import sqrt
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import bsplines as bs
+from .multilevels import knots_to_insert
+from .stencil import (StencilVectorSpace, StencilVector, KronSumMatrix, DeviceContext,
+                      _stream, EPI_STORE, EPI_RESID, EPI_DINV)
+from .kron_product import BandLU, kron_solve_bnd
+from . import solvers
+
+__all__ = ["Transfer", "CoarseSolver", "two_grid", "Hierarchy", "vcycle", "mg_pcg",
+           "fine_knots"]
+
+
+def fine_knots(Tc, ts):
+    """Sorted union of the coarse knots and the inserted ones (mg_jac.py:32-35)."""
+    return np.sort(np.concatenate([np.asarray(Tc, float), np.asarray(ts, float)]), kind="stable")
+
+
+def _gather(src_ptr, dst_ptr, start, coef, n_in, n_out, n_outer, so_in, sa_in, so_out, sa_out,
+            n_inner, accumulate):
+    _lib.check(_lib.lib().poms_axis_gather(
+        src_ptr, dst_ptr, start.data_ptr(), coef.data_ptr(), coef.shape[1], n_in, n_out, n_outer,
+        so_in, sa_in, so_out, sa_out, n_inner, int(accumulate), _stream()), "poms_axis_gather")
+
+
+class _AxisOp:
+    """Row-compressed sparse matrix applied along one axis of a contiguous d-dim array."""
+
+    def __init__(self, start, coef, n_in, device):
+        self.n_out, self.W = coef.shape
+        self.n_in = int(n_in)
+        self.start = torch.as_tensor(np.ascontiguousarray(start, dtype=np.int32), device=device)
+        self.coef = torch.as_tensor(np.ascontiguousarray(coef, dtype=np.float64), device=device)
+
+    def apply(self, src, dst, shape_in, axis, accumulate=False):
+        """dst = op along `axis` of src; tensors are contiguous with shape_in / shape_out."""
+        shape_out = list(shape_in)
+        shape_out[axis] = self.n_out
+        n_outer = int(np.prod(shape_in[:axis])) if axis > 0 else 1
+        n_inner = int(np.prod(shape_in[axis + 1:])) if axis + 1 < len(shape_in) else 1
+        _gather(src.data_ptr(), dst.data_ptr(), self.start, self.coef, self.n_in, self.n_out,
+                n_outer, self.n_in * n_inner, n_inner, self.n_out * n_inner, n_inner, n_inner,
+                accumulate)
+        return tuple(shape_out)
+
+
+class Transfer:
+    """Per-axis knot-insertion transfer between a fine and a coarse tensor-product space."""
+
+    def __init__(self, Tc_axes, Tf_axes, p, device):
+        self.ndim = len(Tc_axes)
+        self.P, self.R = [], []
+        self.P1_rows = []
+        for Tc, Tf in zip(Tc_axes, Tf_axes):
+            nf = len(Tf) - p - 1
+            nc = len(Tc) - p - 1
+            if nf == nc:
+                self.P.append(None)
+                self.R.append(None)
+                self.P1_rows.append(None)
+                continue
+            st, cf, _ = bs.knot_insertion_rows(Tc, Tf, p)
+            stt, cft = bs.rows_transpose(st, cf, nc)
+            self.P.append(_AxisOp(st, cf, nc, device))
+            self.R.append(_AxisOp(stt, cft, nf, device))
+            self.P1_rows.append((st, cf, nc))
+        self.device = device
+
+    def restrict(self, rf, Vc):
+        """r_c = (P1^T (x) .. (x) P1^T) r_f.  Axis 1 first: the largest array is read once,
+        fully coalesced, and every later pass works on a smaller one."""
+        assert rf.space.slab is None or rf.space.slab.size == 1, "use dist.restrict for slabs"
+        rc = StencilVector(Vc)
+        cur = rf.data
+        shape = tuple(rf.space.local_shape)
+        ops = [(ax, op) for ax, op in enumerate(self.R) if op is not None]
+        if not ops:
+            rc.data.copy_(cur)
+            return rc
+        for n, (ax, op) in enumerate(ops):
+            shape_out = list(shape)
+            shape_out[ax] = op.n_out
+            last = n == len(ops) - 1
+            dst = rc.data if last else torch.empty(shape_out, dtype=torch.float64,
+                                                   device=self.device)
+            shape = op.apply(cur, dst, shape, ax)
+            cur = dst
+        return rc
+
+    def prolong_add(self, ec, xf):
+        """x_f += (P1 (x) .. (x) P1) e_c.  Last axis first (small arrays); the final, largest
+        pass along axis 1 accumulates straight into x_f (correction fused, mg_jac.py:112)."""
+        cur = ec.data
+        shape = tuple(ec.space.local_shape)
+        ops = [(ax, op) for ax, op in reversed(list(enumerate(self.P))) if op is not None]
+        if not ops:
+            xf.data.add_(cur)
+            return xf
+        for n, (ax, op) in enumerate(ops):
+            shape_out = list(shape)
+            shape_out[ax] = op.n_out
+            last = n == len(ops) - 1
+            dst = xf.data if last else torch.empty(shape_out, dtype=torch.float64,
+                                                   device=self.device)
+            shape = op.apply(cur, dst, shape, ax, accumulate=last)
+            cur = dst
+        return xf
+
+
+class CoarseSolver:
+    """Exact inverse of a Kronecker-sum operator by fast diagonalisation:
+    K_a Q_a = M_a Q_a L_a, Q_a^T M_a Q_a = I  =>  A^-1 = (x)Q_a . diag(1/sum_a l_a) . (x)Q_a^T.
+    Replaces splu(csc_matrix(Ac)).solve(rc) (mg_jac.py:98-99); the 1-D eigenbases are dense
+    n_c x n_c and are applied as per-axis contractions."""
+
+    def __init__(self, A, device):
+        from scipy.linalg import eigh
+        assert A.form == 1, "fast diagonalisation needs the Kronecker-sum form"
+        self.ndim = A.ndim
+        self.npts = A.npts
+        lam, self.Q, self.Qt = [], [], []
+        for a in range(A.ndim):
+            Kd = bs.band_to_dense(A.Ks[a])
+            Md = bs.band_to_dense(A.Ms[a])
+            w, Q = eigh(0.5 * (Kd + Kd.T), 0.5 * (Md + Md.T))
+            lam.append(w)
+            n = Q.shape[0]
+            z = np.zeros(n, dtype=np.int32)
+            self.Q.append(_AxisOp(z, Q, n, device))
+            self.Qt.append(_AxisOp(z, np.ascontiguousarray(Q.T), n, device))
+        D = 0.0
+        for a in range(A.ndim):
+            t = np.ones(())
+            for c in range(A.ndim):
+                t = np.multiply.outer(t, lam[c] if c == a else np.ones_like(lam[c]))
+            D = D + t
+        self.D = torch.as_tensor(np.ascontiguousarray(D), device=device)
+        self.device = device
+
+    def solve(self, b):
+        """x = A^-1 b (new vector)."""
+        V = b.space
+        shape = tuple(V.local_shape)
+        t0 = torch.empty(shape, dtype=torch.float64, device=self.device)
+        t1 = torch.empty(shape, dtype=torch.float64, device=self.device)
+        cur = b.data
+        bufs = [t0, t1]
+        for a in range(self.ndim):
+            dst = bufs[a % 2]
+            self.Qt[a].apply(cur, dst, shape, a)
+            cur = dst
+        other = bufs[self.ndim % 2]
+        ctx = DeviceContext.get(self.device)
+        _lib.check(_lib.lib().poms_diag_scale(other.data_ptr(), cur.data_ptr(), self.D.data_ptr(),
+                                               cur.numel(), 1.0, None, ctx.ws_ptr, _stream()),
+                   "poms_diag_scale")
+        cur = other
+        x = StencilVector(V)
+        for a in range(self.ndim):
+            last = a == self.ndim - 1
+            dst = x.data if last else (t0 if cur is t1 else t1)
+            self.Q[a].apply(cur, dst, shape, a)
+            cur = dst
+        return x
+
+
+# ==========================================================================================
+# two-grid cycle of the reference scripts
+# ==========================================================================================
+def two_grid(A, transfer, coarse, b, Vc, post="jac", M1=None, M2=None, p=None,
+             pre_maxiter=10, post_maxiter=10, tol=1e-6):
+    """One two-grid cycle in the order of /root/reference/sources/mg_jac.py:85-119
+    (post='jac') or /root/reference/sources/mg_glt.py:84-123 (post='glt')."""
+    ctx = DeviceContext.get(b.space.device)
+    xf, info_pre = solvers.pcg(A, solvers.damped_jacobi, b, tol=tol, maxiter=pre_maxiter)
+    rf = StencilVector(b.space)
+    A.apply(xf, rf, EPI_RESID, b=b, dot_ptr=ctx.sptr(solvers.S_TMP))   # rf = bf - Af.dot(xf)
+    rc = transfer.restrict(rf, Vc)                                     # rc = R.dot(rf)
+    xc = coarse.solve(rc)                                              # splu(Ac).solve(rc)
+    x_corr = xf.copy()
+    transfer.prolong_add(xc, x_corr)                                   # xf = xf + P.dot(xc)
+    if post == "jac":
+        xf2, info_post = solvers.pcg(A, solvers.damped_jacobi, b, x0=x_corr, tol=tol,
+                                     maxiter=post_maxiter)
+    else:
+        xf2, info_post = solvers.pcg_glt(A, M1, M2, b, x0=x_corr, tol=tol, maxiter=p + 1)
+    return dict(x_pre=xf, info_pre=info_pre, r_f=rf, r_c=rc, x_c=xc, x_corr=x_corr,
+                x_post=xf2, info_post=info_post)
+
+
+# ==========================================================================================
+# EXTENSION: multi-level V-cycle and MG-preconditioned CG
+# ==========================================================================================
+def _gen_eig_max(Kb, Tb):
+    """Largest generalised eigenvalue of K x = mu T x for banded SPD 1-D matrices (host)."""
+    n = Kb.shape[0]
+    if n <= 1500:
+        from scipy.linalg import eigh
+        return float(eigh(bs.band_to_dense(Kb), bs.band_to_dense(Tb), eigvals_only=True,
+                          subset_by_index=[n - 1, n - 1])[0])
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.linalg import eigsh
+
+    def sp(band):
+        p = (band.shape[1] - 1) // 2
+        from scipy.sparse import diags
+        return diags([band[max(0, -k):n - max(0, k), k + p] for k in range(-p, p + 1)],
+                     list(range(-p, p + 1)), format="csc")
+    return float(eigsh(sp(Kb), k=1, M=sp(Tb), which="LA", return_eigenvectors=False,
+                       tol=1e-8)[0])
+
+
+class Level:
+    pass
+
+
+class Hierarchy:
+    """Dyadic hierarchy of nested spline spaces for -Lap u + u on [0,1]^d.
+
+    N: elements per axis on the fine level (int or per-axis sequence); every level halves each
+    axis that still has more than `Nc` elements.  smoother: 'glt' | 'jacobi'.
+    """
+
+    def __init__(self, p, N, ndim=None, Nc=8, device="cuda", smoother="glt", nu=1, ratio=4.0,
+                 safety=1.1, slab=None):
+        if np.isscalar(N):
+            N = [int(N)] * int(ndim)
+        self.p, self.ndim = p, len(N)
+        self.device = torch.device(device)
+        self.smoother, self.nu, self.ratio, self.safety = smoother, nu, ratio, safety
+        self.levels = []
+        Ns = list(N)
+        while True:
+            lv = Level()
+            lv.N = list(Ns)
+            lv.knots = [bs.make_open_knots(p, n + p) for n in Ns]
+            lv.A = KronSumMatrix.poisson(p, lv.knots)
+            lv.V = StencilVectorSpace([n + p for n in Ns], [p] * self.ndim,
+                                      [False] * self.ndim, device=self.device,
+                                      slab=slab if not self.levels else None)
+            self.levels.append(lv)
+            if all(n <= Nc for n in Ns):
+                break
+            nxt = [n // 2 if (n > Nc and n % 2 == 0) else n for n in Ns]
+            if nxt == Ns:
+                break
+            Ns = nxt
+        for f, c in zip(self.levels[:-1], self.levels[1:]):
+            f.transfer = Transfer(c.knots, f.knots, p, self.device)
+        self.coarse = CoarseSolver(self.levels[-1].A, self.device)
+        for lv in self.levels[:-1]:
+            self._setup_smoother(lv)
+
+    def _setup_smoother(self, lv):
+        p, d = self.p, self.ndim
+        A = lv.A
+        if self.smoother == "glt":
+            q = max(2 * p - 1, 1)
+            lv.glt_bands = [bs.glt_band(p, n, degree=q) for n in A.npts]
+            lv.glt_lu = [BandLU.from_band(b, self.device) for b in lv.glt_bands]
+            # lambda_max(B^-1 A) ~ max_a mu(K_a) prod_{b != a} mu(M_b): 1-D generalised
+            # eigenvalues wrt T (accurate to ~1 % in 2-D/3-D), times `safety`.
+            muM = [_gen_eig_max(A.mass_bands[a], lv.glt_bands[a]) for a in range(d)]
+            best = 0.0
+            for a in range(d):
+                Kb = A.Ks[a] + (A.mass_bands[a] if a != d - 1 else 0.0)  # K_a + M_a
+                muK = _gen_eig_max(bs.pad_band(Kb, A.P), bs.pad_band(lv.glt_bands[a], A.P))
+                best = max(best, muK * float(np.prod([muM[c] for c in range(d) if c != a])))
+            lv.lmax = self.safety * best
+        elif self.smoother == "jacobi":
+            lv.lmax = self.safety * self._power_lmax_jacobi(lv)
+        else:
+            raise ValueError("smoother must be 'glt' or 'jacobi'")
+        lv.lmin = lv.lmax / self.ratio
+
+    def _power_lmax_jacobi(self, lv, iters=30):
+        """lambda_max(D^-1 A) by power iteration on the device (setup; deterministic start)."""
+        V = lv.V
+        ctx = DeviceContext.get(self.device)
+        g = torch.Generator(device="cpu").manual_seed(1234)
+        v = StencilVector.from_array(V, torch.rand(V.npts, generator=g, dtype=torch.float64)
+                                     .numpy() + 0.5) if V.slab is None else None
+        zero = StencilVector(V)
+        w = StencilVector(V)
+        lam = 1.0
+        for _ in range(iters):
+            # w = -D^-1 (0 - A v) = D^-1 A v
+            lv.A.apply(v, w, EPI_DINV, b=zero, omega=-1.0, dot_ptr=ctx.sptr(solvers.S_TMP))
+            nw = sqrt(float(ctx.scal[solvers.S_TMP].item()))
+            nv = sqrt(v.dot(v))
+            lam = nw / nv
+            v = w * (1.0 / nw)
+        return lam
+
+    # ---- smoothing: nu Chebyshev steps on B^-1 A --------------------------------------------
+    def smooth(self, lv, b, x, zero_guess):
+        A = lv.A
+        V = lv.V
+        L = _lib.lib()
+        ctx = DeviceContext.get(self.device)
+        theta = 0.5 * (lv.lmax + lv.lmin)
+        delta = 0.5 * (lv.lmax - lv.lmin)
+        sigma = theta / delta
+        rho = 1.0 / sigma
+        r = StencilVector(V)
+        z = StencilVector(V) if self.smoother == "glt" else r
+        d = StencilVector(V)
+        for k in range(self.nu):
+            if self.smoother == "glt":
+                if k == 0 and zero_guess:
+                    src = b                                      # r = b - A.0 = b
+                else:
+                    A.apply(x, r, EPI_RESID, b=b)                # r = b - A x
+                    src = r
+                kron_solve_bnd(lv.glt_lu, src, z)                # z = B^-1 r
+            else:
+                if k == 0 and zero_guess:
+                    A.jacobi_first(z, b, 1.0, None)              # z = D^-1 b
+                else:
+                    A.apply(x, z, EPI_DINV, b=b, omega=1.0)      # z = D^-1 (b - A x)
+            if k == 0:
+                c1, c2 = 0.0, 1.0 / theta
+            else:
+                rho_n = 1.0 / (2.0 * sigma - rho)
+                c1, c2 = rho_n * rho, 2.0 * rho_n / delta
+                rho = rho_n
+            _lib.check(L.poms_cheb_update(x.ptr, d.ptr, z.ptr, c1, c2, x.n_owned, _stream()),
+                       "poms_cheb_update")
+        return x
+
+
+def vcycle(h, l, b):
+    """One V(nu,nu) cycle from a zero initial guess on level l; returns a new vector."""
+    lv = h.levels[l]
+    if l == len(h.levels) - 1:
+        return h.coarse.solve(b)
+    x = StencilVector(lv.V)
+    h.smooth(lv, b, x, True)
+    r = StencilVector(lv.V)
+    lv.A.apply(x, r, EPI_RESID, b=b)
+    rc = lv.transfer.restrict(r, h.levels[l + 1].V)
+    ec = vcycle(h, l + 1, rc)
+    lv.transfer.prolong_add(ec, x)
+    h.smooth(lv, b, x, False)
+    return x
+
+
+def mg_pcg(h, b, x0=None, tol=1e-10, maxiter=200, criterion="relative", verbose=False):
+    """MG-preconditioned CG: the reference's `pcg` driver (same operation order) with one V-cycle
+    as `psolve`.  criterion='relative': stop when ||r|| <= tol*||r0|| (the BASELINE metric);
+    criterion='reference': the reference's own mixed rule r.r < tol*||r0||."""
+    A = h.levels[0].A
+
+    def psolve(A_, r):
+        return vcycle(h, 0, r)
+
+    if criterion == "reference":
+        return solvers.pcg(A, psolve, b, x0=x0, tol=tol, maxiter=maxiter, verbose=verbose)
+    return solvers._pcg_driver(A, psolve, b, x0, tol, maxiter, verbose, "MG-PCG solver:",
+                               relative=True)

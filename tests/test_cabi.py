@@ -1,0 +1,64 @@
+"""CPU-side checks of the C-ABI boundary: the shared library loads without a GPU, exports
+every symbol include/poms_b200.h declares, and validates arguments before touching CUDA."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from poms_b200 import _lib
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "poms_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(poms_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "run `python -m poms_b200.build` first"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), "header declares %s but the library does not export it" % n
+    # and the Python binding covers exactly the header
+    assert sorted(_lib.EXPORTS) == names
+
+
+def test_version_and_workspace():
+    L = _lib.lib()
+    assert L.poms_version() >= 100
+    assert L.poms_workspace_bytes() >= 8 * 1024
+
+
+def test_argument_validation_happens_before_cuda():
+    L = _lib.lib()
+    # null x -> -(argument index), no CUDA call is made
+    rc = L.poms_kron_matvec_3d(None, None, None, 4, 4, 4, 4, 16, 0, 0, 3, 1, None, None, None, None,
+                               None, None, 0, 0.0, None, None, None)
+    assert rc == -1
+    assert b"bad argument" in L.poms_last_error()
+    rc = L.poms_kron_matvec_2d(1, 1, None, 4, 4, 2, 0, 0, 3, 1, 1, 1, 1, 1, 0, 0.0, None, None, None)
+    assert rc == -6  # ld < n2
+    rc = L.poms_band_solve_axis(1, 1, 1, 1, 8, 9, 1, 1, 8, 1, 1, None)
+    assert rc == -6  # kl out of range
+    with pytest.raises(_lib.PomsError):
+        _lib.check(rc, "poms_band_solve_axis")
+
+
+def test_no_cpu_path():
+    import torch
+    from poms_b200.stencil import DeviceContext
+    with pytest.raises(_lib.PomsError):
+        DeviceContext.get(torch.device("cpu"))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "poms_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert "import oracle" not in src and "from oracle" not in src, f
+            assert "poms_oracle" not in src, f

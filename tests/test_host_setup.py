@@ -1,0 +1,97 @@
+"""Host-side setup logic of the product (poms_b200/bsplines.py, multilevels.py, stencil.py host
+helpers) against the oracle and the golden vectors.  No GPU needed."""
+import numpy as np
+import pytest
+
+from oracle import poms_oracle as po
+from poms_b200 import bsplines as bs
+from poms_b200.multilevels import knots_to_insert
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+def test_knots_to_insert_golden(golden):
+    g = golden("knots_to_insert")
+    for i in range(int(g["ncases"])):
+        pf, nf, pc, nc = g["case%d_params" % i]
+        Tc, Tf = bs.make_open_knots(pc, nc), bs.make_open_knots(pf, nf)
+        assert np.array_equal(Tc, g["case%d_Tc" % i]) and np.array_equal(Tf, g["case%d_Tf" % i])
+        assert np.array_equal(knots_to_insert(Tf, nf, pf, Tc, nc, pc), g["case%d_ts" % i])
+
+
+@pytest.mark.parametrize("p,N", [(1, 6), (2, 7), (3, 9), (5, 8), (3, 64), (4, 13)])
+def test_assembly_bands(p, N):
+    T = bs.make_open_knots(p, N + p)
+    M, K = bs.assemble_1d_bands(p, T)
+    Mo, Ko = po.assemble_1d(p, T)
+    assert rel(M, po.dense_to_band(Mo, p)) < 1e-13
+    assert rel(K, po.dense_to_band(Ko, p)) < 1e-13
+    assert abs(M.sum() - 1.0) < 1e-13 and abs(K.sum()) < 1e-9
+
+
+def test_assembly_bands_golden_mass(golden):
+    g = golden("assembly_1d")
+    for key in g.files:
+        p, ne = int(key.split("_")[1][1:]), int(key.split("_")[2][2:])
+        M, K = bs.assemble_1d_bands(p, bs.make_open_knots(p, ne + p))
+        assert rel(M, g[key]) < 1e-13
+
+
+@pytest.mark.parametrize("p,nc,nf", [(3, 8, 23), (3, 8, 16), (2, 8, 14), (1, 8, 10), (5, 13, 21),
+                                     (3, 11, 67), (3, 19, 35)])
+def test_insertion_rows_match_boehm(p, nc, nf):
+    Tc, Tf = bs.make_open_knots(p, nc), bs.make_open_knots(p, nf)
+    ts = knots_to_insert(Tf, nf, p, Tc, nc, p)
+    T = np.sort(np.concatenate([Tc, ts]))
+    st, cf, ncol = bs.knot_insertion_rows(Tc, T, p)
+    P1 = bs.rows_to_dense(st, cf, ncol)
+    assert rel(P1, po.insertion_matrix(ts, nc, p, Tc)) < 1e-14
+    assert np.abs(P1.sum(axis=1) - 1.0).max() < 1e-14      # partition of unity
+    stt, cft = bs.rows_transpose(st, cf, ncol)
+    assert np.array_equal(bs.rows_to_dense(stt, cft, P1.shape[0]), P1.T)
+    lo, cd = bs.dense_to_rows(P1)
+    assert np.array_equal(bs.rows_to_dense(lo, cd, ncol), P1)
+
+
+def test_insertion_rows_golden(golden):
+    g = golden("mg_jac_p3_nc8_nf16")
+    st, cf, ncol = bs.knot_insertion_rows(g["Tc"], g["T"], 3)
+    assert rel(bs.rows_to_dense(st, cf, ncol), g["P1"]) < 1e-14
+
+
+def test_band_helpers_and_lapack_layout(golden):
+    g = golden("kron_solve_bnd_nonsym_rect")
+    ab, kl, ku = bs.band_to_lapack(g["A1"])
+    la1, ua1 = g["lu"][:2]
+    assert (kl, ku) == (la1, ua1) and np.array_equal(ab, g["A1_bnd"])
+    lub, kl, ku, piv = bs.band_lu(g["A1"])
+    assert np.array_equal(lub, g["A1_lu"]) and np.array_equal(piv, g["piv1"])
+    A = bs.band_to_dense(g["A1"])
+    assert np.array_equal(bs.dense_to_band(A, 3), g["A1"])
+    assert np.array_equal(bs.pad_band(g["A2"], 4)[:, 2:7], g["A2"])
+    from poms_b200.kron_product import to_bnd
+    b2, la, ua = to_bnd(A)
+    assert (la, ua) == (la1, ua1) and np.array_equal(b2, g["A1_bnd"])
+
+
+def test_glt_band():
+    assert rel(bs.glt_band(3, 9), po.glt_band(3, 9)) < 1e-15
+    assert rel(bs.glt_band(3, 9, degree=5), po.glt_band(3, 9, degree=5)) < 1e-15
+    assert rel(bs.glt_band(5, 12, degree=9), po.glt_band(5, 12, degree=9)) < 1e-14
+    k, v = bs.cardinal_bspline_values(3)
+    assert np.allclose(v[np.abs(k) <= 1], [1 / 6, 4 / 6, 1 / 6])
+
+
+@pytest.mark.parametrize("tag", ["p1_ne16", "p2_ne10", "p3_ne12"])
+def test_kron_sum_host_form_equals_reference_assembly(golden, tag):
+    from poms_b200.stencil import KronSumMatrix
+    g = golden("pcg_jacobi_" + tag)
+    p, ne = int(g["p"]), int(g["ne"])
+    T = bs.make_open_knots(p, ne + p)
+    A = KronSumMatrix.poisson(p, [T, T])
+    assert rel(A.to_stencil_array(), g["A"]) < 1e-12
+    assert rel(A.diagonal_host(), g["A"][:, :, p, p]) < 1e-13
+    assert abs(A[3, 4, 0, 0] - g["A"][3, 4, p, p]) < 1e-15
+    assert abs(A[3, 4, 1, -1] - g["A"][3, 4, p + 1, p - 1]) < 1e-15
