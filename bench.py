@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- the POMS hot path on B200: MG-preconditioned CG to 1e-10 relative residual.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c5|c2|c3|c4|c1] [--impl reference]
+
+A "step" is ONE complete MG-PCG solve (b = 1 on every DOF, x0 = 0) of the synthetic
+-Lap(u)+u problem of the chosen BASELINE config; `value` = DOF / (seconds per solve), inputs
+resident in HBM.  `e2e` is the same solve through the public API with HOST buffers: pinned
+host b -> device, solve, x -> pinned host, all inside the timed region.
+Default config: c5 (3-D, degree 3, 512^3 elements per GPU), the configuration the BASELINE
+metric is quoted on; it fits one GPU.  Under torchrun (N > 1) the grid is slab-partitioned along
+axis 1, 512 element planes per GPU (weak scaling).
+
+--impl reference times the reference's CPU algorithm (oracle port: the reference itself is
+pure Python over an absent third-party package and cannot travel) on the host cores, on a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (ndim, p, elements per axis, description)
+    "c1": (2, 3, 64, "2-D Poisson p=3 64x64"),
+    "c2": (2, 3, 2048, "2-D Poisson p=3 2048x2048"),
+    "c3": (3, 3, 128, "3-D Poisson p=3 128^3"),
+    "c4": (2, 5, 8192, "2-D Poisson p=5 8192x8192"),
+    "c5": (3, 3, 512, "3-D Poisson p=3 512^3"),
+}
+METRIC = "DOF/s to 1e-10 rel. residual (MG-PCG); Kron matvec GB/s vs HBM peak"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_solve(ndim, p, N, tol=1e-10):
+    """One MG-PCG solve with the CPU oracle (restatement of the same algorithm)."""
+    import numpy as np
+    from oracle import poms_oracle as po
+    h = po.MGHierarchy(p, [N] * ndim, smoother="glt", nu=1)
+    b = np.ones(h.levels[0]["A"].npts)
+    t0 = time.perf_counter()
+    x, info = h.mg_pcg(b, tol=tol, maxiter=200)
+    dt = time.perf_counter() - t0
+    return int(np.prod(b.shape)), dt, info
+
+
+def cpu_sample_size(ndim):
+    # bounded sample: ~10-30 s of CPU work
+    return 64 if ndim == 3 else 512
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU algorithm on the host cores (oracle port)."""
+    if rank != 0:
+        return
+    ndim, p, N, desc = CONFIGS[args.config]
+    Ns = min(N, cpu_sample_size(ndim))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        dof, dt, info = cpu_port_solve(ndim, p, Ns)
+        if i >= args.warmup:
+            vals.append(dof / dt)
+        if sum(1.0 / v * dof for v in vals) > 240:
+            break
+    v = sum(vals) / len(vals)
+    cores = 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "DOF/s", "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * dof / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "%s (CPU sample: %d^%d elements, same MG-PCG algorithm)"
+                               % (desc, Ns, ndim), "p": p, "ndim": ndim, "elements_per_axis": Ns,
+                   "iterations": info["niter"]},
+        "cpu_baseline": {"value": v, "unit": "DOF/s", "cores": cores, "kind": "port",
+                         "sample": "%d^%d elements, NumPy/SciPy oracle (single-threaded), "
+                                   "full MG-PCG solve to 1e-10" % (Ns, ndim)},
+        "e2e": {"value": v, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="c5", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--smoother", default="glt", choices=["glt", "jacobi"])
+    ap.add_argument("--nu", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from poms_b200 import _lib, profiling
+    from poms_b200.mg import Hierarchy, mg_pcg
+    from poms_b200.stencil import StencilVector, EPI_RESID
+
+    if args.steps < 1 or args.warmup < 0:
+        raise SystemExit("steps >= 1, warmup >= 0")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    slab = None
+    if world > 1:
+        from poms_b200.dist import Slab
+        dist.init_process_group("nccl", device_id=dev)
+        slab = Slab(dist.group.WORLD, dev)
+    ndim, p, N, desc = CONFIGS[args.config]
+    Ns = [N] * ndim
+    if world > 1:
+        Ns[0] = N * world          # weak scaling: N element planes per GPU along axis 1
+    h = Hierarchy(p, Ns, device=dev, smoother=args.smoother, nu=args.nu, slab=slab)
+    V = h.levels[0].V
+    dof_global = int(np.prod(V.npts))
+    b = StencilVector(V)
+    b.data.fill_(1.0)
+    L = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def solve():
+        return mg_pcg(h, b, tol=1e-10, maxiter=200)
+
+    for _ in range(args.warmup):
+        x, info = solve()
+    # ---- timed region: K solves, device-resident inputs --------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if not args.no_kernel_timing:
+        profiling.enable(True)
+    barrier()
+    l0 = L.poms_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        x, info = solve()
+    e1.record()
+    barrier()
+    launches = L.poms_launch_count() - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    kern = profiling.summary() if profiling.enabled() else {}
+    profiling.enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # true residual of the returned solution (work is not skipped / cached)
+    r = StencilVector(V)
+    h.levels[0].A.apply(x, r, EPI_RESID, b=b)
+    true_rel = (r.dot(r) / b.dot(b)) ** 0.5
+
+    # ---- e2e: host buffers, H2D + solve + D2H inside the timed region -------------------------
+    nloc = V.local_size
+    b_host = torch.ones(V.local_shape, dtype=torch.float64).pin_memory()
+    x_host = torch.empty(V.local_shape, dtype=torch.float64).pin_memory()
+
+    def solve_host():
+        bb = StencilVector(V)
+        bb.data.copy_(b_host, non_blocking=True)
+        xx, inf = mg_pcg(h, bb, tol=1e-10, maxiter=200)
+        x_host.copy_(xx.data, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return inf
+
+    solve_host()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        solve_host()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    steps = args.steps
+    for d in kern.values():
+        d["ms_per_step"] = d["ms"] / steps
+        d["share"] = d["ms"] / (ms * steps) if ms > 0 else 0.0
+    mv_name = "kron_matvec_%dd" % ndim
+    dominant = max(kern, key=lambda k: kern[k]["ms"]) if kern else mv_name
+    roof = None
+    if kern:
+        k = kern[dominant]
+        avg_ms = k["ms"] / k["launches"]
+        achieved = k["bytes"] / k["launches"] / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "launches": k["launches"],
+                "avg_launch_ms": avg_ms, "share_of_step": k["share"],
+                "algorithmic_bytes_per_launch": k["bytes"] / k["launches"]}
+    line = {
+        "metric": METRIC, "value": dof_global / (ms * 1e-3), "unit": "DOF/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc + (" per GPU, slab-partitioned along axis 1" if world > 1
+                                       else ""),
+                   "ndim": ndim, "p": p, "elements": Ns, "dof": dof_global,
+                   "solver": "pcg + V(%d,%d) %s-Chebyshev multigrid, tol 1e-10 relative"
+                             % (args.nu, args.nu, args.smoother),
+                   "iterations": info["niter"], "levels": len(h.levels),
+                   "rel_residual_reported": info["res_norm"] / info["res_norm0"],
+                   "rel_residual_true": true_rel,
+                   "l2_note": "vectors are %.0f MB each, larger than the 126 MB L2"
+                              % (8 * dof_global / world / 1e6)},
+        "gpu_launches": int(launches),
+        "e2e": {"value": dof_global / (ms_e2e * 1e-3), "unit": "DOF/s",
+                "ms_per_step": ms_e2e, "h2d_bytes_per_step": 8 * nloc * world,
+                "d2h_bytes_per_step": 8 * nloc * world},
+        "clocks": clocks,
+        "roofline": roof,
+        "kernels": {k: {"launches": v["launches"], "ms_per_step": round(v["ms_per_step"], 4),
+                        "share": round(v["share"], 4), "gbs": round(v["gbs"], 1)}
+                    for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])},
+    }
+    if mv_name in kern:
+        k = kern[mv_name]
+        line["kron_matvec"] = {"achieved_gbs": k["gbs"], "frac_of_peak": k["gbs"] / peak,
+                               "launches": k["launches"]}
+    if not args.no_cpu_baseline:
+        Nc = min(N, cpu_sample_size(ndim))
+        dofc, dtc, infoc = cpu_port_solve(ndim, p, Nc)
+        line["cpu_baseline"] = {"value": dofc / dtc, "unit": "DOF/s", "cores": 1, "kind": "port",
+                                "host_cores_available": os.cpu_count(),
+                                "sample": "%d^%d elements (%d DOF), one full MG-PCG solve to 1e-10 "
+                                          "with the NumPy/SciPy oracle, %d iterations, %.1f s"
+                                          % (Nc, ndim, dofc, infoc["niter"], dtc)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

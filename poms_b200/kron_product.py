@@ -11,6 +11,7 @@ import torch
 
 from . import _lib
 from . import bsplines as bs
+from . import profiling
 from .stencil import (StencilVector, StencilMatrix, KronSumMatrix, DeviceContext, _stream)
 
 __all__ = ["kron_dot_v1", "kron_dot_v2", "kron_dot", "kron_solve_serial", "kron_solve_par",
@@ -94,7 +95,10 @@ def kron_solve_bnd(factors, Y, X=None):
         X = StencilVector(V)
     src = Y
     for ax, lu in enumerate(lus):
-        _solve_axis(lu, src, X, ax)
+        # algorithmic bytes of one dgbtrs sweep pair: forward (read y, write t) + backward
+        # (read t, write x) = 32 B/DOF unfused; 16 B/DOF is the fused bound
+        with profiling.region("band_solve_axis%d" % (ax + 1), 16 * V.local_size):
+            _solve_axis(lu, src, X, ax)
         src = X
     return X
 

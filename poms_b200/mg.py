@@ -24,6 +24,7 @@ import torch
 
 from . import _lib
 from . import bsplines as bs
+from . import profiling
 from .multilevels import knots_to_insert
 from .stencil import (StencilVectorSpace, StencilVector, KronSumMatrix, DeviceContext,
                       _stream, EPI_STORE, EPI_RESID, EPI_DINV)
@@ -347,8 +348,9 @@ class Hierarchy:
                 rho_n = 1.0 / (2.0 * sigma - rho)
                 c1, c2 = rho_n * rho, 2.0 * rho_n / delta
                 rho = rho_n
-            _lib.check(L.poms_cheb_update(x.ptr, d.ptr, z.ptr, c1, c2, x.n_owned, _stream()),
-                       "poms_cheb_update")
+            with profiling.region("cheb_update", 40 * x.n_owned):
+                _lib.check(L.poms_cheb_update(x.ptr, d.ptr, z.ptr, c1, c2, x.n_owned, _stream()),
+                           "poms_cheb_update")
         return x
 
 
@@ -361,9 +363,11 @@ def vcycle(h, l, b):
     h.smooth(lv, b, x, True)
     r = StencilVector(lv.V)
     lv.A.apply(x, r, EPI_RESID, b=b)
-    rc = lv.transfer.restrict(r, h.levels[l + 1].V)
+    with profiling.region("restrict", 8 * lv.V.local_size, launches=h.ndim):
+        rc = lv.transfer.restrict(r, h.levels[l + 1].V)
     ec = vcycle(h, l + 1, rc)
-    lv.transfer.prolong_add(ec, x)
+    with profiling.region("prolong_add", 16 * lv.V.local_size, launches=h.ndim):
+        lv.transfer.prolong_add(ec, x)
     h.smooth(lv, b, x, False)
     return x
 

@@ -1,0 +1,52 @@
+"""Optional per-kernel CUDA-event timing (used by bench.py for the roofline numbers).
+
+Disabled by default: `region()` is then a no-op.  When enabled, every instrumented launch is
+bracketed by two CUDA events recorded on the launching stream, and `summary()` reports, per
+kernel family, launches, total device time and the algorithmic bytes the caller declared.
+"""
+import contextlib
+
+import torch
+
+_enabled = False
+_records = []
+
+
+def enable(flag=True):
+    global _enabled
+    _enabled = bool(flag)
+    del _records[:]
+
+
+def enabled():
+    return _enabled
+
+
+@contextlib.contextmanager
+def region(name, nbytes=0, launches=1):
+    if not _enabled:
+        yield
+        return
+    a = torch.cuda.Event(enable_timing=True)
+    b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    yield
+    b.record()
+    _records.append((name, a, b, int(nbytes), int(launches)))
+
+
+def summary():
+    """{name: {"launches", "ms", "bytes", "gbs"}} -- call after torch.cuda.synchronize()."""
+    out = {}
+    for name, a, b, nbytes, launches in _records:
+        d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+        d["launches"] += launches
+        d["ms"] += a.elapsed_time(b)
+        d["bytes"] += nbytes
+    for d in out.values():
+        d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+    return out
+
+
+def reset():
+    del _records[:]

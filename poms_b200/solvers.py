@@ -14,6 +14,7 @@ from math import sqrt
 import torch
 
 from . import _lib
+from . import profiling
 from .stencil import (StencilVector, DeviceContext, dot_into, _stream, EPI_STORE, EPI_RESID,
                       EPI_JACOBI)
 
@@ -90,9 +91,10 @@ def _pcg_driver(A, psolve, b, x0, tol, maxiter, verbose, title, relative=False):
         A.apply(p, q, EPI_STORE, dot_ptr=ctx.sptr(S_PQ))
         _reduce(ctx, V, S_PQ)
         # x += alpha p ; r -= alpha q ; r.r   (lines 106-111; alpha = sr / p.q on the device)
-        _lib.check(L.poms_cg_update(x.ptr, r.ptr, p.ptr, q.ptr, x.n_owned, ctx.sptr(cur),
-                                    ctx.sptr(S_PQ), ctx.sptr(S_RR), ctx.ws_ptr, _stream()),
-                   "poms_cg_update")
+        with profiling.region("cg_update", 48 * x.n_owned):
+            _lib.check(L.poms_cg_update(x.ptr, r.ptr, p.ptr, q.ptr, x.n_owned, ctx.sptr(cur),
+                                        ctx.sptr(S_PQ), ctx.sptr(S_RR), ctx.ws_ptr, _stream()),
+                       "poms_cg_update")
         # (line 109 `s = A.dot(r)` is dead: overwritten at 117 or unused after the break)
         nrmr = _read(ctx, V, S_RR)
         hist.append(sqrt(nrmr))
@@ -101,11 +103,13 @@ def _pcg_driver(A, psolve, b, x0, tol, maxiter, verbose, title, relative=False):
             break
         s = psolve(A, r)
         nxt = S_SR1 if cur == S_SR0 else S_SR0
-        dot_into(s, r, ctx.sptr(nxt), ctx)
+        with profiling.region("dot", 16 * x.n_owned):
+            dot_into(s, r, ctx.sptr(nxt), ctx)
         _reduce(ctx, V, nxt)
         # p = s + (sr/srold) p   (lines 119-124)
-        _lib.check(L.poms_p_update(p.ptr, s.ptr, p.n_owned, ctx.sptr(nxt), ctx.sptr(cur),
-                                   _stream()), "poms_p_update")
+        with profiling.region("p_update", 24 * x.n_owned):
+            _lib.check(L.poms_p_update(p.ptr, s.ptr, p.n_owned, ctx.sptr(nxt), ctx.sptr(cur),
+                                       _stream()), "poms_p_update")
         cur = nxt
         if verbose:
             print(template.format(k, sqrt(nrmr)))

@@ -19,6 +19,7 @@ import torch
 
 from . import _lib
 from . import bsplines as bs
+from . import profiling
 
 FORM_SINGLE, FORM_SUM = 0, 1
 EPI_STORE, EPI_RESID, EPI_JACOBI, EPI_DINV = 0, 1, 2, 3
@@ -496,6 +497,12 @@ class KronSumMatrix:
         kp = [t.data_ptr() if t is not None else None for t in k]
         L = _lib.lib()
         bp = b.ptr if b is not None else None
+        # algorithmic bytes: read x, write y (+ read b for the fused residual/Jacobi epilogues)
+        nbytes = (16 if epi == EPI_STORE else 24) * V.local_size
+        with profiling.region("kron_matvec_%dd" % self.ndim, nbytes):
+            self._launch(L, V, x, y, bp, m, kp, epi, omega, dot_ptr, ctx)
+
+    def _launch(self, L, V, x, y, bp, m, kp, epi, omega, dot_ptr, ctx):
         if self.ndim == 2:
             n1, n2 = V.local_shape
             _lib.check(L.poms_kron_matvec_2d(
