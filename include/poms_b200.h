@@ -115,8 +115,11 @@ int poms_diag_scale(double* x, const double* b, const double* d, int64_t n, doub
  * Replaces the per-line dgbtrs of kron_solve_bnd_par (sources/kron_product.py:226,232) and
  * kron_solve_par_bnd_pyccel_{2d,3d} (pyccel/pyccel_functions.py:160,166,229-244).
  * `ab` is the dgbtrf output in LAPACK band storage as a row-major (2kl+ku+1, n) array,
- * `ipiv` the 0-based pivots (int32).  The array is viewed as (n_outer, n, n_inner) with
- * strides (s_outer, s_axis, 1); y -> x (may alias).
+ * `ipiv` the 0-based pivots (int32); ipiv == NULL states that dgbtrf made no row interchange
+ * (ipiv[j] == j: SPD / diagonally dominant bands such as mass and GLT matrices) and selects the
+ * streaming kernels: one thread per line for a strided axis, warp-tiled shared-memory transposition
+ * for the contiguous axis.  The array is viewed as (n_outer, n, n_inner) with strides
+ * (s_outer, s_axis, 1); y -> x (may alias).
  */
 int poms_band_solve_axis(const double* y, double* x, const double* ab, const int32_t* ipiv,
                          int n, int kl, int ku, int64_t n_outer, int64_t s_outer, int64_t s_axis,

@@ -977,14 +977,250 @@ static int band_solve_ku(int ku, const double* y, double* x, const double* ab,
     return 0;
 }
 
+
+// ---- no-pivoting variants (ipiv == NULL): SPD / diagonally dominant bands (mass, GLT) ----------
+// Row-oriented substitution: z_j = y_j - sum_m L[j,j-m] z_{j-m};  x_j = (z_j - sum_m U[j,j+m] x_{j+m}) / U_jj.
+// The updates hit b_j in the same order as LAPACK's column-oriented dgbtrs, so the results agree
+// to the last FMA.
+
+// (a) lines along a STRIDED axis: one thread per line, lanes on the contiguous index (coalesced),
+//     UNR independent loads in flight per thread.
+template <int KL, int KU>
+__global__ void __launch_bounds__(128) band_solve_cols_nopiv_kernel(
+    const double* __restrict__ y, double* __restrict__ x, const double* __restrict__ ab, int n,
+    int64_t n_outer, int64_t s_outer, int64_t s_axis, int64_t n_inner) {
+    constexpr int KD = KL + KU;
+    constexpr int UNR = 8;
+    const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= n_outer * n_inner) return;
+    const int64_t o = line / n_inner, c = line - o * n_inner;
+    const double* yl = y + o * s_outer + c;
+    double* xl = x + o * s_outer + c;
+    double z[KL > 0 ? KL : 1];
+#pragma unroll
+    for (int m = 0; m < KL; ++m) z[m] = 0.0;  // z[m-1] = z_{j-m}
+    for (int j0 = 0; j0 < n; j0 += UNR) {
+        double v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) v[u] = (j0 + u < n) ? yl[(int64_t)(j0 + u) * s_axis] : 0.0;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int j = j0 + u;
+            if (j < n) {
+                double s = v[u];
+#pragma unroll
+                for (int m = KL; m >= 1; --m)
+                    if (j - m >= 0) s = fma(-__ldg(ab + (int64_t)(KD + m) * n + (j - m)), z[m - 1], s);
+                xl[(int64_t)j * s_axis] = s;
+#pragma unroll
+                for (int m = KL - 1; m >= 1; --m) z[m] = z[m - 1];
+                if (KL > 0) z[0] = s;
+            }
+        }
+    }
+    double w[KU > 0 ? KU : 1];
+#pragma unroll
+    for (int m = 0; m < KU; ++m) w[m] = 0.0;  // w[m-1] = x_{j+m}
+    const int nb = (n + UNR - 1) / UNR;
+    for (int b = nb - 1; b >= 0; --b) {
+        const int j0 = b * UNR;
+        double v[UNR], rd[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const bool ok = j0 + u < n;
+            v[u] = ok ? xl[(int64_t)(j0 + u) * s_axis] : 0.0;
+            rd[u] = ok ? 1.0 / __ldg(ab + (int64_t)KD * n + (j0 + u)) : 0.0;
+        }
+#pragma unroll
+        for (int u = UNR - 1; u >= 0; --u) {
+            const int j = j0 + u;
+            if (j < n) {
+                double s = v[u];
+#pragma unroll
+                for (int m = KU; m >= 1; --m)
+                    if (j + m < n) s = fma(-__ldg(ab + (int64_t)(KD - m) * n + (j + m)), w[m - 1], s);
+                s *= rd[u];
+                xl[(int64_t)j * s_axis] = s;
+#pragma unroll
+                for (int m = KU - 1; m >= 1; --m) w[m] = w[m - 1];
+                if (KU > 0) w[0] = s;
+            }
+        }
+    }
+}
+
+// (b) lines along the CONTIGUOUS axis: a warp owns 32 lines and walks them in 32-column tiles that
+//     are staged through shared memory (cp.async double buffering), so global accesses are
+//     coalesced 256-byte rows while lane l runs the recurrence of line l on the transposed tile.
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+#define BSR_WARPS 4
+#define BSR_PITCH 33
+template <int KL, int KU>
+__global__ void __launch_bounds__(32 * BSR_WARPS) band_solve_rows_nopiv_kernel(
+    const double* __restrict__ y, double* __restrict__ x, const double* __restrict__ ab, int n,
+    int64_t n_lines, int64_t s_line) {
+    constexpr int KD = KL + KU;
+    extern __shared__ double smem_bsr[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double* tile0 = smem_bsr + (size_t)wid * 2 * 32 * BSR_PITCH;
+    double* tile1 = tile0 + 32 * BSR_PITCH;
+    const int64_t l0 = ((int64_t)blockIdx.x * BSR_WARPS + wid) * 32;
+    if (l0 >= n_lines) return;
+    const int nl = (int)min((int64_t)32, n_lines - l0);
+    const int nt = (n + 31) / 32;
+    const bool mine = lane < nl;
+
+    auto prefetch = [&](const double* src, double* tile, int t) {
+        const int col = t * 32 + lane;
+        if (col < n) {
+            for (int r = 0; r < nl; ++r) cp_async8(tile + r * BSR_PITCH + lane, src + (l0 + r) * s_line + col);
+        }
+        cp_async_commit();
+    };
+    auto store = [&](double* tile, int t) {
+        const int col = t * 32 + lane;
+        if (col < n) {
+            for (int r = 0; r < nl; ++r) x[(l0 + r) * s_line + col] = tile[r * BSR_PITCH + lane];
+        }
+    };
+
+    // ---------------- forward ----------------
+    double z[KL > 0 ? KL : 1];
+#pragma unroll
+    for (int m = 0; m < KL; ++m) z[m] = 0.0;
+    prefetch(y, tile0, 0);
+    for (int t = 0; t < nt; ++t) {
+        double* cur = (t & 1) ? tile1 : tile0;
+        double* nxt = (t & 1) ? tile0 : tile1;
+        if (t + 1 < nt) prefetch(y, nxt, t + 1); else cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const int jend = min(32, n - t * 32);
+        if (mine) {
+            double* row = cur + lane * BSR_PITCH;
+#pragma unroll 4
+            for (int u = 0; u < jend; ++u) {
+                const int j = t * 32 + u;
+                double s = row[u];
+#pragma unroll
+                for (int m = KL; m >= 1; --m)
+                    if (j - m >= 0) s = fma(-__ldg(ab + (int64_t)(KD + m) * n + (j - m)), z[m - 1], s);
+                row[u] = s;
+#pragma unroll
+                for (int m = KL - 1; m >= 1; --m) z[m] = z[m - 1];
+                if (KL > 0) z[0] = s;
+            }
+        }
+        __syncwarp();
+        store(cur, t);
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+    // ---------------- backward (reads the forward result back from x) ----------------
+    double w[KU > 0 ? KU : 1];
+#pragma unroll
+    for (int m = 0; m < KU; ++m) w[m] = 0.0;
+    prefetch(x, tile0, nt - 1);
+    for (int i = 0; i < nt; ++i) {
+        const int t = nt - 1 - i;
+        double* cur = (i & 1) ? tile1 : tile0;
+        double* nxt = (i & 1) ? tile0 : tile1;
+        if (t - 1 >= 0) prefetch(x, nxt, t - 1); else cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const int jend = min(32, n - t * 32);
+        if (mine) {
+            double* row = cur + lane * BSR_PITCH;
+#pragma unroll 4
+            for (int u = jend - 1; u >= 0; --u) {
+                const int j = t * 32 + u;
+                double s = row[u];
+                const double rd = 1.0 / __ldg(ab + (int64_t)KD * n + j);
+#pragma unroll
+                for (int m = KU; m >= 1; --m)
+                    if (j + m < n) s = fma(-__ldg(ab + (int64_t)(KD - m) * n + (j + m)), w[m - 1], s);
+                s *= rd;
+                row[u] = s;
+#pragma unroll
+                for (int m = KU - 1; m >= 1; --m) w[m] = w[m - 1];
+                if (KU > 0) w[0] = s;
+            }
+        }
+        __syncwarp();
+        store(cur, t);
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+}
+
+template <int KL>
+static int band_solve_nopiv_ku(int ku, const double* y, double* x, const double* ab, int n,
+                               int64_t n_outer, int64_t s_outer, int64_t s_axis, int64_t n_inner,
+                               cudaStream_t st) {
+    const bool rows = (n_inner == 1 && s_axis == 1);
+    const int64_t lines = n_outer * n_inner;
+    const size_t smem = (size_t)BSR_WARPS * 2 * 32 * BSR_PITCH * sizeof(double);
+#define BSN(KU_)                                                                                  \
+    if (rows) {                                                                                   \
+        static bool attr_set = false;                                                             \
+        if (!attr_set) {                                                                          \
+            cudaFuncSetAttribute(band_solve_rows_nopiv_kernel<KL, KU_>,                           \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+            attr_set = true;                                                                      \
+        }                                                                                         \
+        const int grid = (int)((lines + 32 * BSR_WARPS - 1) / (32 * BSR_WARPS));                  \
+        band_solve_rows_nopiv_kernel<KL, KU_><<<grid, 32 * BSR_WARPS, smem, st>>>(y, x, ab, n,    \
+                                                                                  lines, s_outer); \
+    } else {                                                                                      \
+        const int grid = (int)((lines + 127) / 128);                                              \
+        band_solve_cols_nopiv_kernel<KL, KU_><<<grid, 128, 0, st>>>(y, x, ab, n, n_outer,         \
+                                                                     s_outer, s_axis, n_inner);    \
+    }
+    switch (ku) {
+        case 0: BSN(0); break;
+        case 1: BSN(1); break;
+        case 2: BSN(2); break;
+        case 3: BSN(3); break;
+        case 4: BSN(4); break;
+        case 5: BSN(5); break;
+        default: return bad_arg(7, "ku must be 0..5");
+    }
+#undef BSN
+    return 0;
+}
+
 extern "C" int poms_band_solve_axis(const double* y, double* x, const double* ab,
                                     const int32_t* ipiv, int n, int kl, int ku, int64_t n_outer,
                                     int64_t s_outer, int64_t s_axis, int64_t n_inner,
                                     void* stream) {
-    if (!y || !x || !ab || !ipiv) return bad_arg(1, "null pointer");
+    if (!y || !x || !ab) return bad_arg(1, "null pointer");
     if (n < 1 || n_outer < 1 || n_inner < 1) return bad_arg(5, "extent");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    if (!ipiv) {  // factorisation without row interchanges
+        switch (kl) {
+            case 0: rc = band_solve_nopiv_ku<0>(ku, y, x, ab, n, n_outer, s_outer, s_axis, n_inner, st); break;
+            case 1: rc = band_solve_nopiv_ku<1>(ku, y, x, ab, n, n_outer, s_outer, s_axis, n_inner, st); break;
+            case 2: rc = band_solve_nopiv_ku<2>(ku, y, x, ab, n, n_outer, s_outer, s_axis, n_inner, st); break;
+            case 3: rc = band_solve_nopiv_ku<3>(ku, y, x, ab, n, n_outer, s_outer, s_axis, n_inner, st); break;
+            case 4: rc = band_solve_nopiv_ku<4>(ku, y, x, ab, n, n_outer, s_outer, s_axis, n_inner, st); break;
+            case 5: rc = band_solve_nopiv_ku<5>(ku, y, x, ab, n, n_outer, s_outer, s_axis, n_inner, st); break;
+            default: return bad_arg(6, "kl must be 0..5");
+        }
+        if (rc) return rc;
+        CHECK_LAUNCH("poms_band_solve_axis(nopiv)");
+        return 0;
+    }
     switch (kl) {
         case 0: rc = band_solve_ku<0>(ku, y, x, ab, ipiv, n, n_outer, s_outer, s_axis, n_inner, st); break;
         case 1: rc = band_solve_ku<1>(ku, y, x, ab, ipiv, n, n_outer, s_outer, s_axis, n_inner, st); break;

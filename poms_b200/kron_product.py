@@ -64,10 +64,23 @@ class BandLU:
         assert lub.shape[0] == 2 * self.kl + self.ku + 1
         self.ab = torch.as_tensor(np.ascontiguousarray(lub, dtype=np.float64), device=device)
         self.piv = torch.as_tensor(np.ascontiguousarray(piv, dtype=np.int32), device=device)
+        # dgbtrf made no row interchange (SPD / diagonally dominant bands): the streaming
+        # no-pivot kernels apply
+        self.nopiv = bool(np.array_equal(np.asarray(piv), np.arange(self.n)))
+
+    @property
+    def piv_ptr(self):
+        return None if self.nopiv else self.piv.data_ptr()
 
     @classmethod
     def from_band(cls, band, device):
-        return cls(*bs.band_lu(np.asarray(band, dtype=np.float64)), device)
+        """dgbtrf of an (n, 2p+1) band, trimmed to its true bandwidth first."""
+        band = np.asarray(band, dtype=np.float64)
+        p = (band.shape[1] - 1) // 2
+        q = p
+        while q > 0 and not band[:, p - q].any() and not band[:, p + q].any():
+            q -= 1
+        return cls(*bs.band_lu(band[:, p - q:p + q + 1]), device)
 
 
 def _solve_axis(lu, src, dst, axis):
@@ -77,7 +90,7 @@ def _solve_axis(lu, src, dst, axis):
     n_outer = int(np.prod(shape[:axis])) if axis > 0 else 1
     n_inner = int(np.prod(shape[axis + 1:])) if axis + 1 < len(shape) else 1
     _lib.check(_lib.lib().poms_band_solve_axis(
-        src.ptr, dst.ptr, lu.ab.data_ptr(), lu.piv.data_ptr(), n, lu.kl, lu.ku, n_outer,
+        src.ptr, dst.ptr, lu.ab.data_ptr(), lu.piv_ptr, n, lu.kl, lu.ku, n_outer,
         n * n_inner, n_inner, n_inner, _stream()), "poms_band_solve_axis")
 
 
