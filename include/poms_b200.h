@@ -66,6 +66,23 @@ int poms_kron_matvec_3d(const double* x, double* y, const double* b,
                         int epilogue, double omega, double* dot_out, void* ws, void* stream);
 
 /*
+ * Same as poms_kron_matvec_3d plus HOST-side hints that unlock the constant-bank coefficient path
+ * of the TMA kernel: toep_host[axis(0,1,2)][m,k][2p+1] = the interior (Toeplitz) band row of the
+ * matrices of each axis, toep_rng_host = {lo1, hi1, lo2, hi2, lo3, hi3}: rows [lo, hi) of that axis equal
+ * it bit for bit (uniform knots: all rows but the first / last 2p).  NULL = no hint.
+ * The TMA path is taken when x is 16-byte aligned and ld, pld are even; otherwise the generic
+ * kernel runs.  poms_set_force_generic(1) forces the generic kernel (tests / A-B timing).
+ */
+int poms_kron_matvec_3d_ex(const double* x, double* y, const double* b,
+                           int n1, int n2, int n3, int64_t ld, int64_t pld, int glo, int ghi,
+                           int p, int form,
+                           const double* m1, const double* k1, const double* m2, const double* k2,
+                           const double* m3, const double* k3,
+                           int epilogue, double omega, double* dot_out, void* ws, void* stream,
+                           const double* toep_host, const int* toep_rng_host);
+void poms_set_force_generic(int flag);
+
+/*
  * Full (non-separable) 2-D stencil mat-vec: y[i1,i2] = sum_{k1,k2} S[i1,i2,k1,k2] x[i1+k1-p1,i2+k2-p2]
  * = spl StencilMatrix.dot (slides/content.tex:285-290; sources/solvers.py:85).  S is
  * (n1, n2, 2p1+1, 2p2+1) row-major.  Same epilogues; diag = S[i1,i2,p1,p2].

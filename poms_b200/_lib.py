@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpoms_b200.so")
+LIB_PATH = os.environ.get("POMS_B200_LIB", os.path.join(HERE, "libpoms_b200.so"))
 
 _vp, _i, _l, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 
@@ -17,6 +17,10 @@ _PROTOS = {
                                      _vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp]),
     "poms_kron_matvec_3d": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _i,
                                      _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp]),
+    "poms_kron_matvec_3d_ex": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _i,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp,
+                                        _vp, _vp]),
+    "poms_set_force_generic": (None, [_i]),
     "poms_stencil_matvec_2d": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _l, _i, _i, _i, _i,
                                         _i, _d, _vp, _vp, _vp]),
     "poms_cg_update": (C.c_int, [_vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp]),

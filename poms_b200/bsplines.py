@@ -68,7 +68,7 @@ def _all_basis(T, p, spans, x):
     return vals, np.moveaxis(ders, 0, 1)
 
 
-def assemble_1d_bands(p, T):
+def assemble_1d_bands(p, T, toeplitz_interior=True):
     """1-D mass and stiffness bands (n, 2p+1) on knot vector T, Gauss-Legendre with p+1
     points per element (exact): the v_m / v_s integrals of
     /root/reference/sources/matrix_assembler.py:59-74."""
@@ -89,7 +89,24 @@ def assemble_1d_bands(p, T):
         for jl in range(p + 1):
             np.add.at(M, (rows, jl - il + p), Me[:, il, jl])
             np.add.at(K, (rows, jl - il + p), Ke[:, il, jl])
+    if toeplitz_interior and n > 4 * p + 1 and _is_uniform_open(T, p):
+        # On a uniform open knot vector the functions p .. n-1-p are translates of one B-spline, so
+        # rows 2p .. n-2p-1 are mathematically identical; quadrature at different abscissae leaves
+        # them equal only to ~1 ulp.  Make them bit-identical (copy the middle row): the kernels
+        # can then take interior coefficients from the constant bank instead of memory.
+        mid = n // 2
+        M[2 * p:n - 2 * p] = M[mid]
+        K[2 * p:n - 2 * p] = K[mid]
     return M, K
+
+
+def _is_uniform_open(T, p):
+    """True if T is a clamped knot vector with equally spaced simple interior knots."""
+    n = len(T) - p - 1
+    if np.any(T[:p + 1] != T[0]) or np.any(T[n:] != T[-1]):
+        return False
+    h = np.diff(T[p:n + 1])
+    return bool(np.all(h > 0) and np.max(np.abs(h - h.mean())) <= 8 * np.finfo(float).eps * abs(T[-1] - T[0]))
 
 
 def knot_insertion_rows(Tc, Tf, p):

@@ -17,7 +17,9 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = SRC + [os.path.join(ROOT, "include", "poms_b200.h")]
+    csrc = os.path.join(HERE, "csrc")
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [
+        os.path.join(ROOT, "include", "poms_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 

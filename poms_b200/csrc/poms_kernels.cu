@@ -43,6 +43,19 @@ extern "C" const char* poms_last_error(void) { return g_err; }
 extern "C" int64_t poms_launch_count(void) { return g_launches; }
 
 // ------------------------------------------------------------------------------------------
+// cp.async helpers (Ampere-style asynchronous global -> shared copies, 8 bytes per thread)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ------------------------------------------------------------------------------------------
 // deterministic grid reduction
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
@@ -356,12 +369,36 @@ static int pick_chunk(int n1, int64_t tiles, int p) {
     return chunk;
 }
 
+#include "poms_matvec3d_tma.cuh"
+
+extern "C" int poms_kron_matvec_3d_ex(const double* x, double* y, const double* b, int n1, int n2,
+                                      int n3, int64_t ld, int64_t pld, int glo, int ghi, int p,
+                                      int form, const double* m1, const double* k1,
+                                      const double* m2, const double* k2, const double* m3,
+                                      const double* k3, int epilogue, double omega,
+                                      double* dot_out, void* ws, void* stream,
+                                      const double* toep_host, const int* toep_rng_host);
+
 extern "C" int poms_kron_matvec_3d(const double* x, double* y, const double* b, int n1, int n2,
                                    int n3, int64_t ld, int64_t pld, int glo, int ghi, int p,
                                    int form, const double* m1, const double* k1,
                                    const double* m2, const double* k2, const double* m3,
                                    const double* k3, int epilogue, double omega,
                                    double* dot_out, void* ws, void* stream) {
+    return poms_kron_matvec_3d_ex(x, y, b, n1, n2, n3, ld, pld, glo, ghi, p, form, m1, k1, m2, k2,
+                                  m3, k3, epilogue, omega, dot_out, ws, stream, nullptr, nullptr);
+}
+
+static int g_force_generic = 0;
+extern "C" void poms_set_force_generic(int flag) { g_force_generic = flag; }
+
+extern "C" int poms_kron_matvec_3d_ex(const double* x, double* y, const double* b, int n1, int n2,
+                                      int n3, int64_t ld, int64_t pld, int glo, int ghi, int p,
+                                      int form, const double* m1, const double* k1,
+                                      const double* m2, const double* k2, const double* m3,
+                                      const double* k3, int epilogue, double omega,
+                                      double* dot_out, void* ws, void* stream,
+                                      const double* toep_host, const int* toep_rng_host) {
     if (!x) return bad_arg(1, "x");
     if (!y) return bad_arg(2, "y");
     if (epilogue != POMS_EPI_STORE && !b) return bad_arg(3, "b required by epilogue");
@@ -372,7 +409,19 @@ extern "C" int poms_kron_matvec_3d(const double* x, double* y, const double* b, 
     if (!m1 || !m2 || !m3) return bad_arg(13, "band pointers");
     if (form == POMS_FORM_SUM && (!k1 || !k2 || !k3)) return bad_arg(14, "k bands");
     if (dot_out && !ws) return bad_arg(22, "ws");
+    if (form != POMS_FORM_SINGLE && form != POMS_FORM_SUM) return bad_arg(12, "form");
+    if (p < 1 || p > 5) return bad_arg(11, "p must be 1..5");
     MV3 a{x, y, b, n1, n2, n3, ld, pld, glo, ghi, m1, k1, m2, k2, m3, k3, omega, dot_out, ws, 0};
+    if (!g_force_generic) {
+        // fast path: TMA-staged pipeline (needs 16-byte aligned rows); 1 = not applicable
+        const int trc = try_matvec3d_tma(a, p, form, epilogue, toep_host, toep_rng_host,
+                                         (cudaStream_t)stream);
+        if (trc == 0) {
+            CHECK_LAUNCH("poms_kron_matvec_3d(tma)");
+            return 0;
+        }
+        if (trc != 1) return trc;
+    }
     const int g3 = (n3 + 63) / 64, g2 = (n2 + 15) / 16;
     a.chunk = pick_chunk(n1, (int64_t)g3 * g2, p);
     const int g1 = (n1 + a.chunk - 1) / a.chunk;
@@ -1052,16 +1101,6 @@ __global__ void __launch_bounds__(128) band_solve_cols_nopiv_kernel(
 // (b) lines along the CONTIGUOUS axis: a warp owns 32 lines and walks them in 32-column tiles that
 //     are staged through shared memory (cp.async double buffering), so global accesses are
 //     coalesced 256-byte rows while lane l runs the recurrence of line l on the transposed tile.
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
-}
-
 #define BSR_WARPS 4
 #define BSR_PITCH 33
 template <int KL, int KU>

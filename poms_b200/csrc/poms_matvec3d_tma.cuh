@@ -1,0 +1,447 @@
+// poms_matvec3d_tma.cuh -- K1 (3-D) fast path: TMA-staged, mbarrier-pipelined Kronecker mat-vec.
+// Included by poms_kernels.cu (single translation unit; uses its reduction / rot_scatter helpers).
+//
+// Per CTA: a 16 x 64 tile of axes (2,3), marching along axis 1.  For every input plane one elected
+// thread issues ONE cp.async.bulk.tensor.3d (TMA) that lands the halo'd (16+2p) x (64+2p) tile in a
+// shared-memory ring, zero-filled outside the domain by the hardware; an mbarrier signals arrival.
+// The ring is 4 deep: three planes of prefetch are in flight ahead of the consumer (one plane was
+// measured to leave the TMA latency exposed: 3.0 ms vs the generic kernel's 3.6 ms at 512^3).
+// su/sv (axis-3 results) are double-buffered, so there is ONE __syncthreads per plane.
+// Coefficients: axis 3 per-thread registers; axes 1 and 2 come from the kernel-parameter constant
+// bank when the rows involved are Toeplitz-interior (uniform knots: all but 2p rows per end),
+// otherwise from shared / global memory (CTA-uniform branch).
+#pragma once
+#include <cuda.h>
+
+struct MV3T {
+    MV3 a;
+    double t1m[11], t1k[11], t2m[11], t2k[11], t3m[11], t3k[11];  // interior (Toeplitz) band rows
+    int lo1, hi1, lo2, hi2, lo3, hi3;            // rows [lo, hi) of each axis equal to them
+    int dot_add;
+};
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"((unsigned)__cvta_generic_to_shared(bar))
+        : "memory");
+}
+
+template <int P>
+struct MV3TCfg {
+    static constexpr int W = 2 * P + 1;
+    static constexpr int T3 = 64, TY = 4, E = 4, T2 = TY * E;
+    // TMA needs (innermost start coordinate * 8 B) 16-byte aligned (measured: an odd fp64
+    // coordinate raises "illegal instruction").  Tiles therefore start at column 64*bx - (p&1):
+    // the halo'd box then starts at the EVEN column 64*bx - (p&1) - p, and inside the tile the
+    // inputs of the output-column pair (2l, 2l+1) are the 16-byte aligned columns 2l .. 2l+2p+1.
+    static constexpr int SH = P & 1;
+    static constexpr int R2 = T2 + 2 * P, C3 = T3 + 2 * P + 2 * SH;   // even
+    static constexpr int PD = 2;        // prefetch distance (planes in flight ahead of the consumer)
+    static constexpr int NST = PD + 1;  // ring depth
+    static constexpr int STAGE_BYTES = ((R2 * C3 * 8 + 127) / 128) * 128;
+    static constexpr int SU_DOUBLES = R2 * T3;
+    static constexpr size_t smem_bytes(bool two) {
+        return (size_t)NST * STAGE_BYTES + (size_t)(two ? 4 : 2) * SU_DOUBLES * 8 +
+               (size_t)2 * T2 * W * 8 + 16 * 8 /*mbar*/ + 32 * 8 /*red*/ +
+               (size_t)2 * T2 * T3 * 8 /* epilogue prefetch slots (b, x) */;
+    }
+};
+
+#ifndef POMS_MV3_MINB
+#define POMS_MV3_MINB 2
+#endif
+template <int P, int FORM, int EPI>
+__global__ void __launch_bounds__(256, (P <= 3 ? POMS_MV3_MINB : 1))
+kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MV3T g) {
+    using C = MV3TCfg<P>;
+    constexpr int W = C::W, T3 = C::T3, TY = C::TY, E = C::E, T2 = C::T2, R2 = C::R2, C3 = C::C3,
+                  NST = C::NST, SH = C::SH, PD = C::PD;
+    constexpr bool TWO = (FORM == POMS_FORM_SUM);
+    constexpr int NX = 2 * P + 2;  // inputs of one output-column pair
+    const MV3& a = g.a;
+    // carve the dynamic shared memory with typed pointers (no integer round trip: the compiler
+    // must see the shared address space, otherwise it emits generic LD/ST)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double* const ring = reinterpret_cast<double*>(smem_raw);
+    double* const su = ring + (size_t)NST * (C::STAGE_BYTES / 8);
+    double* const sv = su + 2 * C::SU_DOUBLES;
+    double* const c2m = su + (TWO ? 4 : 2) * C::SU_DOUBLES;
+    double* const c2k = c2m + T2 * W;
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(c2k + T2 * W);
+    double* const red = reinterpret_cast<double*>(mbar + 16);
+    double* const pfb = red + 32;            // per-thread private slots: rhs of the output plane
+    double* const pfx = pfb + T2 * T3;       //                           x at the output points
+
+    const int tid = threadIdx.x;
+    const int tx = tid & (T3 - 1), ty = tid / T3;      // stage 2/3 mapping: column tx, rows ty*E..
+    const int lane = tid & 31, wid = tid >> 5;          // stage 1 mapping: column pair `lane`
+    const int i3_0 = blockIdx.x * T3 - SH, i2_0 = blockIdx.y * T2;
+    const int c_lo = blockIdx.z * a.chunk;
+    const int c_hi = min(a.n1, c_lo + a.chunk);
+    const int i3 = i3_0 + tx;
+    const bool v3 = i3 >= 0 && i3 < a.n3;
+    const bool toep2 = (i2_0 >= g.lo2) && (i2_0 + T2 <= g.hi2);
+    // stage-1 columns of this lane and whether both are Toeplitz-interior rows of M3 / K3
+    const int ca = i3_0 + 2 * lane, cb = ca + 1;
+    const bool toep3 = (ca >= g.lo3) && (cb < g.hi3);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) mbar_init(mbar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    if (!toep2) {
+        for (int t = tid; t < T2 * W; t += blockDim.x) {
+            const int r = t / W, k = t - r * W, i2 = i2_0 + r;
+            c2m[t] = i2 < a.n2 ? a.m2[(int64_t)i2 * W + k] : 0.0;
+            if (TWO) c2k[t] = i2 < a.n2 ? a.k2[(int64_t)i2 * W + k] : 0.0;
+        }
+    }
+    double dA[E], dB[E];
+    if (EPI >= POMS_EPI_JACOBI) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i2 = i2_0 + ty * E + e;
+            const bool ok = v3 && i2 < a.n2;
+            const double m2d = ok ? a.m2[(int64_t)i2 * W + P] : 1.0;
+            const double m3d = ok ? a.m3[(int64_t)i3 * W + P] : 1.0;
+            dA[e] = m2d * m3d;
+            dB[e] = 0.0;
+            if (TWO) {
+                const double k2d = ok ? a.k2[(int64_t)i2 * W + P] : 0.0;
+                const double k3d = ok ? a.k3[(int64_t)i3 * W + P] : 0.0;
+                dB[e] = k2d * m3d + m2d * k3d;
+            }
+        }
+    }
+    double acc[E][W];
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc[e][k] = 0.0;
+    double dsum = 0.0;
+
+    const int start = c_lo - P, end = c_hi + P;
+    auto valid = [&](int j1) { return j1 >= -a.glo && j1 < a.n1 + a.ghi; };
+    __syncthreads();  // barriers initialised, c2m/c2k staged
+    if (tid == 0) {
+#pragma unroll
+        for (int d = 0; d < PD; ++d) {
+            if (start + d < end && valid(start + d)) {
+                mbar_expect_tx(mbar + d, R2 * C3 * 8);
+                tma_load_3d(ring + (size_t)d * (C::STAGE_BYTES / 8), &tmap, i3_0 - P, i2_0 - P,
+                            start + d + a.glo, mbar + d);
+            }
+        }
+    }
+    // per-thread offset of its first output point inside a plane
+    const int64_t poff = (int64_t)(i2_0 + ty * E) * a.ld + i3;
+    unsigned phase_bits = 0;
+    int u = 0, st = 0;
+#pragma unroll 1
+    for (int j1 = start; j1 < end; ++j1) {
+        const int t = j1 - start;
+        const bool have = valid(j1);
+        const int i1 = j1 - P;
+        const bool emit = (i1 >= c_lo && i1 < c_hi);
+        // Prefetch what the epilogue of the output plane completed by this input plane needs, with
+        // cp.async into per-thread shared slots: no registers are held across stages 1-3 (keeping
+        // them in registers made ptxas spill and stall on the load right away).
+        constexpr bool NEED_B = (EPI != POMS_EPI_STORE);
+        const bool need_x = (EPI == POMS_EPI_STORE && a.dot_out) || EPI == POMS_EPI_JACOBI;
+        if (emit && v3) {
+            const int64_t o = (int64_t)i1 * a.pld + poff;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                if ((i2_0 + ty * E + e) < a.n2) {
+                    if (NEED_B) cp_async8(pfb + (ty * E + e) * T3 + tx, a.b + o + (int64_t)e * a.ld);
+                    if (need_x) cp_async8(pfx + (ty * E + e) * T3 + tx, a.x + o + (int64_t)e * a.ld);
+                }
+            }
+        }
+        cp_async_commit();
+        double* const sub = su + (t & 1) * C::SU_DOUBLES;
+        double* const svb = sv + (t & 1) * C::SU_DOUBLES;
+        if (have) {
+            mbar_wait(mbar + st, (phase_bits >> st) & 1u);
+            phase_bits ^= (1u << st);
+            const double* const sx = ring + (size_t)st * (C::STAGE_BYTES / 8);
+            // ---- stage 1: band pass along axis 3; lane = pair of output columns ----
+#pragma unroll 1
+            for (int r = wid; r < R2; r += 8) {
+                double xr[NX];
+                const double2* src = reinterpret_cast<const double2*>(sx + r * C3 + 2 * lane);
+#pragma unroll
+                for (int q = 0; q < NX / 2; ++q) {
+                    const double2 v2 = src[q];
+                    xr[2 * q] = v2.x;
+                    xr[2 * q + 1] = v2.y;
+                }
+                double ua = 0.0, ub = 0.0, va = 0.0, vb = 0.0;
+                if (toep3) {
+#pragma unroll
+                    for (int k = 0; k < W; ++k) {
+                        ua = fma(g.t3m[k], xr[k], ua);
+                        ub = fma(g.t3m[k], xr[k + 1], ub);
+                        if (TWO) {
+                            va = fma(g.t3k[k], xr[k], va);
+                            vb = fma(g.t3k[k], xr[k + 1], vb);
+                        }
+                    }
+                } else {  // boundary columns: coefficients of these two rows of M3 / K3
+                    const bool oka = ca >= 0 && ca < a.n3, okb = cb >= 0 && cb < a.n3;
+#pragma unroll
+                    for (int k = 0; k < W; ++k) {
+                        const double ma = oka ? __ldg(a.m3 + (int64_t)ca * W + k) : 0.0;
+                        const double mb = okb ? __ldg(a.m3 + (int64_t)cb * W + k) : 0.0;
+                        ua = fma(ma, xr[k], ua);
+                        ub = fma(mb, xr[k + 1], ub);
+                        if (TWO) {
+                            const double ka = oka ? __ldg(a.k3 + (int64_t)ca * W + k) : 0.0;
+                            const double kb = okb ? __ldg(a.k3 + (int64_t)cb * W + k) : 0.0;
+                            va = fma(ka, xr[k], va);
+                            vb = fma(kb, xr[k + 1], vb);
+                        }
+                    }
+                }
+                *reinterpret_cast<double2*>(sub + r * T3 + 2 * lane) = make_double2(ua, ub);
+                if (TWO) *reinterpret_cast<double2*>(svb + r * T3 + 2 * lane) = make_double2(va, vb);
+            }
+        }
+        __syncthreads();
+        // ---- producer: plane j1+PD into the slot of plane j1-1 (every thread is past its stage 1)
+        if (tid == 0 && j1 + PD < end && valid(j1 + PD)) {
+            const int sn = (st + PD) % NST;
+            mbar_expect_tx(mbar + sn, R2 * C3 * 8);
+            tma_load_3d(ring + (size_t)sn * (C::STAGE_BYTES / 8), &tmap, i3_0 - P, i2_0 - P,
+                        j1 + PD + a.glo, mbar + sn);
+        }
+        double ta[E], tb[E], vout[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) ta[e] = tb[e] = 0.0;
+        if (have) {
+            // ---- stage 2: band pass along axis 2, scatter form (no register window) ----
+            const double* const up = sub + (ty * E) * T3 + tx;
+            const double* const vp = svb + (ty * E) * T3 + tx;
+            if (toep2) {
+#pragma unroll
+                for (int r = 0; r < E + 2 * P; ++r) {
+                    const double uv = up[r * T3];
+                    const double vv = TWO ? vp[r * T3] : 0.0;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int k = r - e;
+                        if (k >= 0 && k < W) {
+                            ta[e] = fma(g.t2m[k], uv, ta[e]);
+                            if (TWO) {
+                                tb[e] = fma(g.t2k[k], uv, tb[e]);
+                                tb[e] = fma(g.t2m[k], vv, tb[e]);
+                            }
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < E + 2 * P; ++r) {
+                    const double uv = up[r * T3];
+                    const double vv = TWO ? vp[r * T3] : 0.0;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int k = r - e;
+                        if (k >= 0 && k < W) {
+                            const double cm = c2m[(ty * E + e) * W + k];
+                            ta[e] = fma(cm, uv, ta[e]);
+                            if (TWO) {
+                                tb[e] = fma(c2k[(ty * E + e) * W + k], uv, tb[e]);
+                                tb[e] = fma(cm, vv, tb[e]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // ---- stage 3: rotating axis-1 partial sums ----
+        const bool toep1 = have && (j1 - P >= g.lo1) && (j1 + P < g.hi1);
+        if (toep1) {
+            rot_scatter<W, E, TWO>(u, acc, ta, tb, *(const double(*)[W]) g.t1k, *(const double(*)[W]) g.t1m, vout);
+        } else {
+            double c1k[W], c1m[W];
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
+                const int o1 = j1 + P - k;
+                const bool ok = have && o1 >= 0 && o1 < a.n1;
+                if (TWO) {
+                    c1k[k] = ok ? __ldg(a.k1 + (int64_t)o1 * W + k) : 0.0;
+                    c1m[k] = ok ? __ldg(a.m1 + (int64_t)o1 * W + k) : 0.0;
+                } else {
+                    c1k[k] = ok ? __ldg(a.m1 + (int64_t)o1 * W + k) : 0.0;
+                    c1m[k] = 0.0;
+                }
+            }
+            rot_scatter<W, E, TWO>(u, acc, ta, tb, c1k, c1m, vout);
+        }
+        // ---- epilogue: output plane i1 = j1 - P ----
+        cp_async_wait<0>();
+        if (emit) {
+            const int64_t o = (int64_t)i1 * a.pld + poff;
+            double dg1 = 0.0, dg2 = 0.0;
+            if (EPI >= POMS_EPI_JACOBI) {
+                dg1 = TWO ? __ldg(a.k1 + (int64_t)i1 * W + P) : __ldg(a.m1 + (int64_t)i1 * W + P);
+                dg2 = TWO ? __ldg(a.m1 + (int64_t)i1 * W + P) : 0.0;
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                if (v3 && (i2_0 + ty * E + e) < a.n2) {
+                    const int64_t idx = o + (int64_t)e * a.ld;
+                    const double v = vout[e];
+                    if (EPI == POMS_EPI_STORE) {
+                        a.y[idx] = v;
+                        if (a.dot_out) dsum = fma(pfx[(ty * E + e) * T3 + tx], v, dsum);
+                    } else if (EPI == POMS_EPI_RESID) {
+                        const double rr = pfb[(ty * E + e) * T3 + tx] - v;
+                        a.y[idx] = rr;
+                        dsum = fma(rr, rr, dsum);
+                    } else {
+                        const double dg = TWO ? dg1 * dA[e] + dg2 * dB[e] : dg1 * dA[e];
+                        const double dr = a.omega * (pfb[(ty * E + e) * T3 + tx] - v) / dg;
+                        a.y[idx] = (EPI == POMS_EPI_JACOBI) ? pfx[(ty * E + e) * T3 + tx] + dr : dr;
+                        dsum = fma(dr, dr, dsum);
+                    }
+                }
+            }
+        }
+        u = (u + 1 == W) ? 0 : u + 1;
+        st = (st + 1 == NST) ? 0 : st + 1;
+    }
+    if (a.dot_out) {
+        const double tot = block_sum(dsum, red);
+        const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        grid_sum_finish(tot, a.dot_out, a.ws, nb, bid, red);
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+template <int P, int FORM, int EPI>
+static int launch_mv3_tma_inst(const CUtensorMap& tm, const MV3T& g, dim3 grid, cudaStream_t st) {
+    const size_t smem = MV3TCfg<P>::smem_bytes(FORM == POMS_FORM_SUM);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kron_matvec3d_tma_kernel<P, FORM, EPI>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(tma)");
+        attr_set = true;
+    }
+    kron_matvec3d_tma_kernel<P, FORM, EPI><<<grid, 256, smem, st>>>(tm, g);
+    return 0;
+}
+template <int P, int FORM>
+static int launch_mv3_tma_epi(const CUtensorMap& tm, const MV3T& g, int epi, dim3 grid, cudaStream_t st) {
+    switch (epi) {
+        case POMS_EPI_STORE: return launch_mv3_tma_inst<P, FORM, POMS_EPI_STORE>(tm, g, grid, st);
+        case POMS_EPI_RESID: return launch_mv3_tma_inst<P, FORM, POMS_EPI_RESID>(tm, g, grid, st);
+        case POMS_EPI_JACOBI: return launch_mv3_tma_inst<P, FORM, POMS_EPI_JACOBI>(tm, g, grid, st);
+        case POMS_EPI_DINV: return launch_mv3_tma_inst<P, FORM, POMS_EPI_DINV>(tm, g, grid, st);
+        default: return bad_arg(19, "epilogue");
+    }
+}
+template <int P>
+static int launch_mv3_tma(const CUtensorMap& tm, const MV3T& g, int form, int epi, dim3 grid, cudaStream_t st) {
+    if (form == POMS_FORM_SINGLE) return launch_mv3_tma_epi<P, POMS_FORM_SINGLE>(tm, g, epi, grid, st);
+    return launch_mv3_tma_epi<P, POMS_FORM_SUM>(tm, g, epi, grid, st);
+}
+
+// returns 0 on success, 1 if the TMA path does not apply (caller falls back to the generic kernel),
+// other values are errors
+static int try_matvec3d_tma(const MV3& a0, int p, int form, int epilogue, const double* toep, const int* toep_rng,
+                            cudaStream_t st) {
+    if (((uintptr_t)a0.x & 15) || (a0.ld & 1) || (a0.pld & 1)) return 1;
+    if (a0.n3 < 8 || a0.n2 < 4) return 1;  // tiny grids: generic kernel
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return 1;
+    const int W = 2 * p + 1;
+    MV3T g;
+    g.a = a0;
+    g.lo1 = g.hi1 = g.lo2 = g.hi2 = g.lo3 = g.hi3 = 0;
+    g.dot_add = 0;
+    for (int k = 0; k < 11; ++k) g.t1m[k] = g.t1k[k] = g.t2m[k] = g.t2k[k] = g.t3m[k] = g.t3k[k] = 0.0;
+    if (toep && toep_rng) {
+        // toep: [axis][m|k][W] for axes 1, 2, 3 ; toep_rng: [axis][lo, hi)
+        for (int k = 0; k < W; ++k) {
+            g.t1m[k] = toep[(0 * 2 + 0) * W + k];
+            g.t1k[k] = toep[(0 * 2 + 1) * W + k];
+            g.t2m[k] = toep[(1 * 2 + 0) * W + k];
+            g.t2k[k] = toep[(1 * 2 + 1) * W + k];
+            g.t3m[k] = toep[(2 * 2 + 0) * W + k];
+            g.t3k[k] = toep[(2 * 2 + 1) * W + k];
+        }
+        g.lo1 = toep_rng[0];
+        g.hi1 = toep_rng[1];
+        g.lo2 = toep_rng[2];
+        g.hi2 = toep_rng[3];
+        g.lo3 = toep_rng[4];
+        g.hi3 = toep_rng[5];
+    }
+    const int sh = p & 1;
+    const int g3 = (a0.n3 + sh + 63) / 64, g2 = (a0.n2 + 15) / 16;
+    g.a.chunk = pick_chunk(a0.n1, (int64_t)g3 * g2, p);
+    const int g1 = (a0.n1 + g.a.chunk - 1) / g.a.chunk;
+    if ((int64_t)g3 * g2 * g1 > POMS_MAX_PARTIALS) return 1;
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {(cuuint64_t)a0.n3, (cuuint64_t)a0.n2, (cuuint64_t)(a0.n1 + a0.glo + a0.ghi)};
+    cuuint64_t strides[2] = {(cuuint64_t)a0.ld * 8, (cuuint64_t)a0.pld * 8};
+    cuuint32_t box[3] = {(cuuint32_t)(64 + 2 * p + 2 * sh), (cuuint32_t)(16 + 2 * p), 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    void* gaddr = (void*)(a0.x - (int64_t)a0.glo * a0.pld);
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, gaddr, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 1;
+    dim3 grid(g3, g2, g1);
+    int rc;
+    switch (p) {
+        case 1: rc = launch_mv3_tma<1>(tm, g, form, epilogue, grid, st); break;
+        case 2: rc = launch_mv3_tma<2>(tm, g, form, epilogue, grid, st); break;
+        case 3: rc = launch_mv3_tma<3>(tm, g, form, epilogue, grid, st); break;
+        case 4: rc = launch_mv3_tma<4>(tm, g, form, epilogue, grid, st); break;
+        case 5: rc = launch_mv3_tma<5>(tm, g, form, epilogue, grid, st); break;
+        default: return bad_arg(11, "p must be 1..5");
+    }
+    return rc;
+}

@@ -84,14 +84,22 @@ class BandLU:
 
 
 def _solve_axis(lu, src, dst, axis):
-    shape = tuple(src.space.local_shape)
+    V = src.space
+    shape = tuple(V.local_shape)
+    ld = V.ld
+    nd = len(shape)
     n = shape[axis]
     assert n == lu.n, "factor size does not match the axis"
-    n_outer = int(np.prod(shape[:axis])) if axis > 0 else 1
-    n_inner = int(np.prod(shape[axis + 1:])) if axis + 1 < len(shape) else 1
+    if axis == nd - 1:            # contiguous axis: one line per row of the pitched array
+        n_outer, s_outer, s_axis, n_inner = int(np.prod(shape[:-1])), ld, 1, 1
+    elif axis == 0:               # slowest axis: lines are (rest of the array) apart
+        rest = int(np.prod(shape[1:-1])) * ld if nd > 1 else 1
+        n_outer, s_outer, s_axis, n_inner = 1, n * rest, rest, rest
+    else:                         # middle axis of a 3-D array
+        n_outer, s_outer, s_axis, n_inner = shape[0], shape[1] * ld, ld, ld
     _lib.check(_lib.lib().poms_band_solve_axis(
         src.ptr, dst.ptr, lu.ab.data_ptr(), lu.piv_ptr, n, lu.kl, lu.ku, n_outer,
-        n * n_inner, n_inner, n_inner, _stream()), "poms_band_solve_axis")
+        s_outer, s_axis, n_inner, _stream()), "poms_band_solve_axis")
 
 
 def kron_solve_bnd(factors, Y, X=None):

@@ -56,16 +56,38 @@ class _AxisOp:
         self.start = torch.as_tensor(np.ascontiguousarray(start, dtype=np.int32), device=device)
         self.coef = torch.as_tensor(np.ascontiguousarray(coef, dtype=np.float64), device=device)
 
-    def apply(self, src, dst, shape_in, axis, accumulate=False):
-        """dst = op along `axis` of src; tensors are contiguous with shape_in / shape_out."""
+    def apply(self, src, dst, shape_in, ld_in, ld_out, axis, accumulate=False):
+        """dst = op along `axis` of src.  src/dst are pitched arrays: logical shape `shape_in`
+        (resp. with n_out along `axis`), last-dimension pitch ld_in / ld_out, pad columns zero."""
+        nd = len(shape_in)
         shape_out = list(shape_in)
         shape_out[axis] = self.n_out
-        n_outer = int(np.prod(shape_in[:axis])) if axis > 0 else 1
-        n_inner = int(np.prod(shape_in[axis + 1:])) if axis + 1 < len(shape_in) else 1
+        if axis == nd - 1:
+            n_outer = int(np.prod(shape_in[:-1])) if nd > 1 else 1
+            so_in, so_out, sa_in, sa_out, n_inner = ld_in, ld_out, 1, 1, 1
+        elif axis == 0:
+            assert ld_in == ld_out
+            rest = int(np.prod(shape_in[1:-1])) * ld_in
+            n_outer, so_in, so_out, sa_in, sa_out, n_inner = 1, 0, 0, rest, rest, rest
+        else:
+            assert ld_in == ld_out
+            n_outer = shape_in[0]
+            so_in, so_out = shape_in[1] * ld_in, self.n_out * ld_in
+            sa_in = sa_out = n_inner = ld_in
         _gather(src.data_ptr(), dst.data_ptr(), self.start, self.coef, self.n_in, self.n_out,
-                n_outer, self.n_in * n_inner, n_inner, self.n_out * n_inner, n_inner, n_inner,
-                accumulate)
+                n_outer, so_in, sa_in, so_out, sa_out, n_inner, accumulate)
         return tuple(shape_out)
+
+
+def _pitch(n):
+    return n + (n & 1)
+
+
+def _tmp(shape, ld, device, zero=True):
+    """Pitched temporary.  zero=False when the producing kernel writes the pad column too (every
+    pass along a non-contiguous axis does: it maps the zero pad of its input)."""
+    alloc = torch.zeros if zero else torch.empty
+    return alloc(tuple(shape[:-1]) + (ld,), dtype=torch.float64, device=device)
 
 
 class Transfer:
@@ -95,39 +117,45 @@ class Transfer:
         fully coalesced, and every later pass works on a smaller one."""
         assert rf.space.slab is None or rf.space.slab.size == 1, "use dist.restrict for slabs"
         rc = StencilVector(Vc)
-        cur = rf.data
+        cur, ld = rf.flat, rf.ld
         shape = tuple(rf.space.local_shape)
         ops = [(ax, op) for ax, op in enumerate(self.R) if op is not None]
         if not ops:
-            rc.data.copy_(cur)
+            rc.flat.copy_(cur)
             return rc
+        nd = len(shape)
         for n, (ax, op) in enumerate(ops):
             shape_out = list(shape)
             shape_out[ax] = op.n_out
             last = n == len(ops) - 1
-            dst = rc.data if last else torch.empty(shape_out, dtype=torch.float64,
-                                                   device=self.device)
-            shape = op.apply(cur, dst, shape, ax)
-            cur = dst
+            ld_out = _pitch(op.n_out) if ax == nd - 1 else ld
+            dst = rc.flat if last else _tmp(shape_out, ld_out, self.device, zero=(ax == nd - 1))
+            if last:
+                assert ld_out == rc.ld
+            shape = op.apply(cur, dst, shape, ld, ld_out, ax)
+            cur, ld = dst, ld_out
         return rc
 
     def prolong_add(self, ec, xf):
         """x_f += (P1 (x) .. (x) P1) e_c.  Last axis first (small arrays); the final, largest
         pass along axis 1 accumulates straight into x_f (correction fused, mg_jac.py:112)."""
-        cur = ec.data
+        cur, ld = ec.flat, ec.ld
         shape = tuple(ec.space.local_shape)
         ops = [(ax, op) for ax, op in reversed(list(enumerate(self.P))) if op is not None]
         if not ops:
-            xf.data.add_(cur)
+            xf.flat.add_(cur)
             return xf
+        nd = len(shape)
         for n, (ax, op) in enumerate(ops):
             shape_out = list(shape)
             shape_out[ax] = op.n_out
             last = n == len(ops) - 1
-            dst = xf.data if last else torch.empty(shape_out, dtype=torch.float64,
-                                                   device=self.device)
-            shape = op.apply(cur, dst, shape, ax, accumulate=last)
-            cur = dst
+            ld_out = _pitch(op.n_out) if ax == nd - 1 else ld
+            dst = xf.flat if last else _tmp(shape_out, ld_out, self.device, zero=(ax == nd - 1))
+            if last:
+                assert ld_out == xf.ld
+            shape = op.apply(cur, dst, shape, ld, ld_out, ax, accumulate=last)
+            cur, ld = dst, ld_out
         return xf
 
 
@@ -158,20 +186,24 @@ class CoarseSolver:
             for c in range(A.ndim):
                 t = np.multiply.outer(t, lam[c] if c == a else np.ones_like(lam[c]))
             D = D + t
-        self.D = torch.as_tensor(np.ascontiguousarray(D), device=device)
+        ld = _pitch(D.shape[-1])
+        Dp = np.ones(D.shape[:-1] + (ld,))          # pad column: 1 so that 0/1 stays 0
+        Dp[..., :D.shape[-1]] = D
+        self.D = torch.as_tensor(np.ascontiguousarray(Dp), device=device)
         self.device = device
 
     def solve(self, b):
         """x = A^-1 b (new vector)."""
         V = b.space
         shape = tuple(V.local_shape)
-        t0 = torch.empty(shape, dtype=torch.float64, device=self.device)
-        t1 = torch.empty(shape, dtype=torch.float64, device=self.device)
-        cur = b.data
+        ld = V.ld
+        t0 = _tmp(shape, ld, self.device)
+        t1 = _tmp(shape, ld, self.device)
+        cur = b.flat
         bufs = [t0, t1]
         for a in range(self.ndim):
             dst = bufs[a % 2]
-            self.Qt[a].apply(cur, dst, shape, a)
+            self.Qt[a].apply(cur, dst, shape, ld, ld, a)
             cur = dst
         other = bufs[self.ndim % 2]
         ctx = DeviceContext.get(self.device)
@@ -182,8 +214,8 @@ class CoarseSolver:
         x = StencilVector(V)
         for a in range(self.ndim):
             last = a == self.ndim - 1
-            dst = x.data if last else (t0 if cur is t1 else t1)
-            self.Q[a].apply(cur, dst, shape, a)
+            dst = x.flat if last else (t0 if cur is t1 else t1)
+            self.Q[a].apply(cur, dst, shape, ld, ld, a)
             cur = dst
         return x
 

@@ -109,6 +109,11 @@ class StencilVectorSpace:
         self.glo = p1 if (self.slab is not None and self.slab.rank > 0) else 0
         self.ghi = p1 if (self.slab is not None and self.slab.rank < self.slab.size - 1) else 0
         self.local_shape = tuple(e - s + 1 for s, e in zip(self.starts, self.ends))
+        # row pitch (doubles): even, so that every row starts 16-byte aligned (TMA global strides,
+        # 128-bit loads).  The pad column, if any, is kept at zero by every kernel.
+        n_last = self.local_shape[-1]
+        self.ld = n_last + (n_last & 1) if self.ndim >= 2 else n_last
+        self.pitched_shape = self.local_shape[:-1] + (self.ld,)
 
     @property
     def cart(self):
@@ -120,7 +125,13 @@ class StencilVectorSpace:
 
     @property
     def local_size(self):
+        """Owned DOFs."""
         return int(np.prod(self.local_shape))
+
+    @property
+    def flat_size(self):
+        """Doubles in the owned storage range (includes the zero pad column)."""
+        return int(np.prod(self.pitched_shape))
 
     def zeros(self):
         return StencilVector(self)
@@ -133,12 +144,13 @@ class StencilVectorSpace:
 class StencilVector:
     def __init__(self, V, _buf=None):
         self._space = V
-        shape = (V.glo + V.local_shape[0] + V.ghi,) + V.local_shape[1:]
+        shape = (V.glo + V.local_shape[0] + V.ghi,) + V.pitched_shape[1:]
         if _buf is None:
             _buf = torch.zeros(shape, dtype=torch.float64, device=V.device)
         assert tuple(_buf.shape) == shape and _buf.is_contiguous()
         self._buf = _buf
-        self.data = _buf[V.glo:V.glo + V.local_shape[0]]
+        self.flat = _buf[V.glo:V.glo + V.local_shape[0]]          # owned planes, pitched
+        self.data = self.flat[..., :V.local_shape[-1]]             # logical (n1, .., n_last) view
 
     # ---- spl-compatible surface ---------------------------------------------------------
     @property
@@ -237,19 +249,20 @@ class StencilVector:
     @property
     def ptr(self):
         """Device pointer of the first OWNED entry."""
-        return self.data.data_ptr()
+        return self.flat.data_ptr()
 
     @property
     def n_owned(self):
-        return self._space.local_size
+        """Length of the contiguous owned storage range (BLAS-1 kernels run over it)."""
+        return self._space.flat_size
 
     @property
     def ld(self):
-        return self._space.local_shape[-1]
+        return self._space.ld
 
     @property
     def pld(self):
-        s = self._space.local_shape
+        s = self._space.pitched_shape
         return s[-1] * s[-2]
 
     def zero_(self):
@@ -412,6 +425,7 @@ class StencilMatrix:
         d = StencilVector(V)
         p1, p2 = self.pads
         loc = np.ascontiguousarray(self._data[V.starts[0]:V.ends[0] + 1, :, p1, p2])
+        d.flat.fill_(1.0)          # pad column: 0/1 keeps the pad at zero
         d.data.copy_(torch.as_tensor(loc, device=V.device))
         return d
 
@@ -471,6 +485,32 @@ class KronSumMatrix:
         A.mass_bands = Ms
         return A
 
+    def _toeplitz(self):
+        """Interior (Toeplitz) rows of the axis-1 and axis-2 bands: host arrays handed to the 3-D
+        TMA kernel, which then takes those coefficients from the kernel-parameter constant bank.
+        Rows [lo, hi) of BOTH bands of an axis are bit-identical to the middle row (uniform knots:
+        all rows except the first/last 2p)."""
+        if getattr(self, "_toep", None) is None:
+            W = 2 * self.P + 1
+            coef = np.zeros((self.ndim, 2, W))
+            rng = np.zeros(2 * self.ndim, dtype=np.int32)
+            for a in range(self.ndim):
+                m = self.Ms[a]
+                k = self.Ks[a] if self.Ks is not None else np.zeros_like(m)
+                n = m.shape[0]
+                mid = n // 2
+                same = np.all(m == m[mid], axis=1) & np.all(k == k[mid], axis=1)
+                lo = mid
+                while lo > 0 and same[lo - 1]:
+                    lo -= 1
+                hi = mid + 1
+                while hi < n and same[hi]:
+                    hi += 1
+                coef[a, 0], coef[a, 1] = m[mid], k[mid]
+                rng[2 * a], rng[2 * a + 1] = lo, hi
+            self._toep = (np.ascontiguousarray(coef), rng)
+        return self._toep
+
     def _bands(self, V):
         """Device band pointers for the rows a space owns (axis-1 rows are the slab's)."""
         key = (V.starts[0], V.ends[0], str(V.device))
@@ -511,10 +551,16 @@ class KronSumMatrix:
                 ctx.ws_ptr, _stream()), "poms_kron_matvec_2d")
         else:
             n1, n2, n3 = V.local_shape
-            _lib.check(L.poms_kron_matvec_3d(
+            coef, rng = self._toeplitz()
+            rng = rng.copy()
+            # axis-1 rows are the slab's: shift the global interior range to local row numbers
+            rng[0] = max(0, int(rng[0]) - V.starts[0])
+            rng[1] = min(n1, int(rng[1]) - V.starts[0])
+            _lib.check(L.poms_kron_matvec_3d_ex(
                 x.ptr, y.ptr, bp, n1, n2, n3, x.ld, x.pld, V.glo, V.ghi, self.P, self.form,
                 m[0].data_ptr(), kp[0], m[1].data_ptr(), kp[1], m[2].data_ptr(), kp[2], epi,
-                float(omega), dot_ptr, ctx.ws_ptr, _stream()), "poms_kron_matvec_3d")
+                float(omega), dot_ptr, ctx.ws_ptr, _stream(), coef.ctypes.data, rng.ctypes.data),
+                "poms_kron_matvec_3d_ex")
 
     def dot(self, v):
         out = StencilVector(v.space)
