@@ -282,7 +282,7 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         // ---- stage 3: rotating axis-1 partial sums ----
         const bool toep1 = have && (j1 - P >= g.lo1) && (j1 + P < g.hi1);
         if (toep1) {
-            rot_scatter<W, E, TWO>(u, acc, ta, tb, *(const double(*)[W]) g.t1k, *(const double(*)[W]) g.t1m, vout);
+            rot_scatter<W, E, TWO>(u, acc, ta, tb, *(const double(*)[W])(TWO ? g.t1k : g.t1m), *(const double(*)[W]) g.t1m, vout);
         } else {
             double c1k[W], c1m[W];
 #pragma unroll

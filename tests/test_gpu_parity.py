@@ -151,7 +151,9 @@ def test_operator_epilogues_vs_oracle(dev, p, N):
     assert np.abs(_arr(Y) - (Bh - Yo) / D).max() < 1e-12 * np.abs(dr).max() * 1.5
     # jacobi(): x = b / diag
     from poms_b200.solvers import jacobi
-    assert rel(_arr(jacobi(A, B)), Bh / D) < 1e-14
+    # (the product copies the middle band row into every Toeplitz-interior row, a <= 1e-14
+    # relative change of the 1-D matrices w.r.t. the per-element quadrature of the oracle)
+    assert rel(_arr(jacobi(A, B)), Bh / D) < 1e-13
     # plain .dot returns a fresh vector and leaves x alone
     assert rel(_arr(A.dot(X)), Yo) < 1e-13 and np.array_equal(_arr(X), Xh)
 
