@@ -1,0 +1,379 @@
+"""Slab partition of the tensor grid along axis 1 (the slowest axis) across the GPUs of one box.
+
+Replaces the reference's MPI layer for the hot path:
+  * `update_ghost_regions` (spl; /root/reference/sources/kron_product.py:76,87, solvers.py:162,215)
+        -> `Slab.exchange`: p contiguous planes to each neighbour (NCCL send/recv; the slab axis
+           is the slowest one, so a halo is one contiguous block and needs no pack kernel);
+  * the allreduce inside `StencilVector.dot` -> `Slab.allreduce_sum` on a device scalar;
+  * one `Allgatherv` PER LINE in kron_solve_par / kron_solve_bnd_par
+    (/root/reference/sources/kron_product.py:156,224) -> a SPIKE partitioned banded solve: every
+    slab solves its own diagonal block, ONE all-gather of the 2q interface planes, a tiny replicated
+    reduced system, and a correction that only touches the planes where the (exponentially
+    decaying) spikes are above rounding;
+  * `comm.allreduce(rc)` of the coarse residual (/root/reference/sources/mg_jac.py:95) ->
+    `Slab.allgather_planes` at the level where the hierarchy becomes replicated.
+
+Every method takes plain torch tensors whose first dimension is the plane index, so the
+communication logic runs unchanged on CPU tensors with the gloo backend (tests/test_dist_gloo.py).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def block_bounds(n, size, rank):
+    """Inclusive [s, e] of the `rank`-th of `size` nearly equal contiguous blocks of range(n)."""
+    base, rem = divmod(n, size)
+    s = rank * base + min(rank, rem)
+    e = s + base + (1 if rank < rem else 0) - 1
+    return s, e
+
+
+class Slab:
+    def __init__(self, group=None, device=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.size = dist.get_world_size(self.group)
+        self.device = device
+
+    # ---- partition ---------------------------------------------------------------------------
+    def bounds(self, n, rank=None):
+        return block_bounds(n, self.size, self.rank if rank is None else rank)
+
+    def table(self, n):
+        return [block_bounds(n, self.size, r) for r in range(self.size)]
+
+    # ---- collectives -------------------------------------------------------------------------
+    def allreduce_sum(self, t):
+        if self.size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def _peer(self, r):
+        return dist.get_global_rank(self.group, r) if self.group is not dist.group.WORLD else r
+
+    def exchange_planes(self, buf, n_own, glo, ghi, width):
+        """Fill the ghost planes of `buf` (planes: [glo ghosts | n_own owned | ghi ghosts]) with the
+        neighbours' outermost `width` owned planes."""
+        if self.size == 1:
+            return
+        ops = []
+        lo_nb, hi_nb = self.rank - 1, self.rank + 1
+        if lo_nb >= 0:
+            assert glo == width and n_own >= width
+            ops.append(dist.P2POp(dist.isend, buf[glo:glo + width], self._peer(lo_nb), self.group))
+            ops.append(dist.P2POp(dist.irecv, buf[0:glo], self._peer(lo_nb), self.group))
+        if hi_nb < self.size:
+            assert ghi == width and n_own >= width
+            ops.append(dist.P2POp(dist.isend, buf[glo + n_own - width:glo + n_own],
+                                  self._peer(hi_nb), self.group))
+            ops.append(dist.P2POp(dist.irecv, buf[glo + n_own:glo + n_own + ghi],
+                                  self._peer(hi_nb), self.group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def exchange(self, v):
+        """Halo exchange of a StencilVector (p planes per neighbour)."""
+        V = v.space
+        self.exchange_planes(v._buf, V.local_shape[0], V.glo, V.ghi, V.pads[0])
+
+    def gather_planes(self, own, table, need):
+        """Planes need[0]..need[1] (global numbering, inclusive) of a plane-partitioned array of
+        which this rank holds `own` = planes table[rank]; the missing ones come from the lower /
+        upper neighbour.  `need_of(r)` must be the same function on every rank: pass the table of
+        needs as need = [(lo, hi) for every rank]."""
+        s, e = table[self.rank]
+        lo, hi = need[self.rank]
+        assert lo <= s and hi >= e
+        out = own.new_empty((hi - lo + 1,) + tuple(own.shape[1:]))
+        out[s - lo:e - lo + 1] = own
+        if self.size == 1:
+            assert lo == s and hi == e
+            return out
+        ops = []
+        r = self.rank
+        if r > 0:
+            ps, pe = table[r - 1]
+            plo, phi = need[r - 1]
+            assert lo >= ps, "needs planes beyond the direct neighbour"
+            if lo < s:                       # I need [lo, s-1] from below
+                ops.append(dist.P2POp(dist.irecv, out[0:s - lo], self._peer(r - 1), self.group))
+            if phi > pe:                     # the lower neighbour needs [pe+1, phi] from me
+                assert phi <= e
+                ops.append(dist.P2POp(dist.isend, own[0:phi - pe].contiguous(),
+                                      self._peer(r - 1), self.group))
+        if r < self.size - 1:
+            ns, ne = table[r + 1]
+            nlo, nhi = need[r + 1]
+            assert hi <= ne, "needs planes beyond the direct neighbour"
+            if hi > e:
+                ops.append(dist.P2POp(dist.irecv, out[e - lo + 1:], self._peer(r + 1), self.group))
+            if nlo < ns:                     # the upper neighbour needs [nlo, ns-1] from me
+                assert nlo >= s
+                ops.append(dist.P2POp(dist.isend, own[nlo - s:].contiguous(),
+                                      self._peer(r + 1), self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return out
+
+    def allgather_planes(self, own, table):
+        """Full array (all planes, every rank) from its plane-partitioned pieces."""
+        if self.size == 1:
+            return own
+        n = table[-1][1] + 1
+        full = own.new_empty((n,) + tuple(own.shape[1:]))
+        sizes = [e - s + 1 for s, e in table]
+        if len(set(sizes)) == 1:
+            dist.all_gather_into_tensor(full, own.contiguous(), group=self.group)
+            return full
+        # uneven blocks: pad to the largest one (the gathered levels are small)
+        mx = max(sizes)
+        padded = own.new_zeros((mx,) + tuple(own.shape[1:]))
+        padded[:own.shape[0]] = own
+        stack = own.new_empty((self.size * mx,) + tuple(own.shape[1:]))
+        dist.all_gather_into_tensor(stack, padded, group=self.group)
+        for q, (s, e) in enumerate(table):
+            full[s:e + 1] = stack[q * mx:q * mx + (e - s + 1)]
+        return full
+
+
+# ==========================================================================================
+# plan of the axis-1 grid transfer between two slab-partitioned (or partitioned -> replicated) levels
+# ==========================================================================================
+def _row_extent(start, coef):
+    """Per row: first and last column holding a non-zero coefficient."""
+    W = coef.shape[1]
+    nz = coef != 0.0
+    first = np.where(nz.any(axis=1), nz.argmax(axis=1), 0)
+    last = np.where(nz.any(axis=1), W - 1 - nz[:, ::-1].argmax(axis=1), 0)
+    return start + first, start + last
+
+
+def slab_transfer_plan(st, cf, nc, size, coarse_distributed):
+    """Host-side plan for applying P1 (rows (st, cf): fine row i <- coarse cols st[i]+w) and
+    R1 = P1^T along the partitioned axis.  For every rank q:
+      need_f[q]  fine planes [lo, hi] its owned coarse rows read (restriction),
+      R0[q]      (start_local, coef) of those rows relative to plane lo,
+      need_c[q]  coarse planes its owned fine rows read (prolongation; None when the coarse level
+                 is replicated and every rank already holds all of them),
+      P0[q]      (start_local, coef, n_in)."""
+    from . import bsplines as bs
+    nf = len(st)
+    stt, cft = bs.rows_transpose(st, cf, nc)
+    tf = [block_bounds(nf, size, q) for q in range(size)]
+    tc = [block_bounds(nc, size, q) for q in range(size)]
+    f_first, f_last = _row_extent(stt, cft)
+    c_first, c_last = _row_extent(st, cf)
+    plan = dict(tf=tf, tc=tc, need_f=[], need_c=[] if coarse_distributed else None, R0=[], P0=[])
+    for q in range(size):
+        cs, ce = tc[q]
+        fs, fe = tf[q]
+        lo = int(min(f_first[cs:ce + 1].min(), fs))
+        hi = int(max(f_last[cs:ce + 1].max(), fe))
+        plan["need_f"].append((lo, hi))
+        plan["R0"].append((stt[cs:ce + 1] - lo, cft[cs:ce + 1], hi - lo + 1))
+        if coarse_distributed:
+            lo = int(min(c_first[fs:fe + 1].min(), cs))
+            hi = int(max(c_last[fs:fe + 1].max(), ce))
+            plan["need_c"].append((lo, hi))
+            plan["P0"].append((st[fs:fe + 1] - lo, cf[fs:fe + 1], hi - lo + 1))
+        else:
+            plan["P0"].append((st[fs:fe + 1], cf[fs:fe + 1], nc))
+    return plan
+
+
+# ==========================================================================================
+# SPIKE: banded solve along the partitioned axis
+# ==========================================================================================
+class SpikeSetup:
+    """Host-side setup of the partitioned solve T x = y for a banded matrix T (half-bandwidth q)
+    whose rows are split into `table` blocks.  With x~_r = T_rr^-1 y_r,
+        x_r = x~_r - W_r x_{r-1}^{bot} - V_r x_{r+1}^{top}
+    (top / bot = first / last q entries).  Stacking the top and bottom q rows of every block gives a
+    2qG x 2qG system S z = z~ that is the same for every line; Sinv is applied as a dense
+    contraction.  V_r, W_r decay exponentially away from the interface for the diagonally dominant
+    SPD bands of this code (mass, GLT): rows below `tol` relative are dropped."""
+
+    def __init__(self, band, table, tol=1e-17):
+        from . import bsplines as bs
+        band = np.asarray(band, dtype=np.float64)
+        p = (band.shape[1] - 1) // 2
+        q = p
+        while q > 0 and not band[:, p - q].any() and not band[:, p + q].any():
+            q -= 1
+        self.q = q
+        band = band[:, p - q:p + q + 1]
+        n = band.shape[0]
+        G = len(table)
+        self.G, self.n, self.table = G, n, table
+        self.local_bands, self.V, self.W = [], [], []
+        S = np.eye(2 * q * G)
+        for r, (s, e) in enumerate(table):
+            nl = e - s + 1
+            assert nl >= 2 * q, "a slab needs at least 2q planes"
+            lb = band[s:e + 1].copy()
+            # entries that couple to other blocks are not part of the diagonal block
+            for k in range(-q, q + 1):
+                i = np.arange(nl)
+                out = (i + k < 0) | (i + k >= nl)
+                lb[out, k + q] = 0.0
+            self.local_bands.append(lb)
+            from scipy.linalg import solve_banded
+            ab = np.zeros((2 * q + 1, nl))
+            for k in range(-q, q + 1):
+                i = np.arange(max(0, -k), min(nl, nl - k))
+                ab[q - k, i + k] = lb[i, k + q]
+            B = np.zeros((nl, q))      # coupling to the first q entries of block r+1
+            C = np.zeros((nl, q))      # coupling to the last q entries of block r-1
+            for i in range(nl):
+                for k in range(-q, q + 1):
+                    j = s + i + k
+                    if j > e and j < n:
+                        B[i, j - (e + 1)] = band[s + i, k + q]
+                    if j < s and j >= 0:
+                        C[i, j - (s - q)] = band[s + i, k + q]
+            V = solve_banded((q, q), ab, B) if r < G - 1 else np.zeros((nl, q))
+            W = solve_banded((q, q), ab, C) if r > 0 else np.zeros((nl, q))
+            self.V.append(V)
+            self.W.append(W)
+            # reduced system rows of block r: [top_r (q) ; bot_r (q)]
+            o = 2 * q * r
+            if r > 0:
+                S[o:o + q, o - q:o] += W[:q]                 # top_r  + W^top  bot_{r-1}
+                S[o + q:o + 2 * q, o - q:o] += W[nl - q:]    # bot_r  + W^bot  bot_{r-1}
+            if r < G - 1:
+                S[o:o + q, o + 2 * q:o + 3 * q] += V[:q]             # top_r + V^top top_{r+1}
+                S[o + q:o + 2 * q, o + 2 * q:o + 3 * q] += V[nl - q:]
+        self.Sinv = np.linalg.inv(S)
+        # truncated spikes: number of planes from the interface where they are above rounding
+        def depth(M, from_top):
+            a = np.abs(M).max(axis=1)
+            a = a if from_top else a[::-1]
+            nz = np.nonzero(a > tol * max(a.max(), 1e-300))[0]
+            return int(nz[-1]) + 1 if len(nz) else 0
+        self.mW = [depth(W, True) for W in self.W]
+        self.mV = [depth(V, False) for V in self.V]
+
+
+def spike_solve_host(setup, y_blocks):
+    """Reference implementation of the partitioned solve on the host (tests): y_blocks[r] is the
+    (n_r, m) block of right-hand sides of slab r; returns the x blocks."""
+    from scipy.linalg import solve_banded
+    q, G = setup.q, setup.G
+    xt = []
+    for r in range(G):
+        lb = setup.local_bands[r]
+        nl = lb.shape[0]
+        ab = np.zeros((2 * q + 1, nl))
+        for k in range(-q, q + 1):
+            i = np.arange(max(0, -k), min(nl, nl - k))
+            ab[q - k, i + k] = lb[i, k + q]
+        xt.append(solve_banded((q, q), ab, y_blocks[r]))
+    zt = np.concatenate([np.concatenate([x[:q], x[-q:]]) for x in xt])
+    z = setup.Sinv @ zt
+    out = []
+    for r in range(G):
+        x = xt[r].copy()
+        o = 2 * q * r
+        if r > 0:
+            x -= setup.W[r] @ z[o - q:o]
+        if r < G - 1:
+            x -= setup.V[r] @ z[o + 2 * q:o + 3 * q]
+        out.append(x)
+    return out
+
+
+_spike_cache = {}
+
+
+def _spike_for(lu, V):
+    """SPIKE setup + device operators of one axis-1 factor for the partition of space V (cached)."""
+    from .kron_product import BandLU
+    from .mg import _AxisOp
+    slab = V.slab
+    key = (id(lu), V.npts[0], slab.size, slab.rank, str(V.device))
+    ent = _spike_cache.get(key)
+    if ent is not None:
+        return ent
+    if getattr(lu, "band", None) is None:
+        raise NotImplementedError(
+            "slab-partitioned Kronecker solve needs the band matrix itself (BandLU.from_band); "
+            "a bare dgbtrf factorisation [A_bnd, la, ua, piv] cannot be re-partitioned")
+    table = slab.table(V.npts[0])
+    st = SpikeSetup(lu.band, table)
+    q, G, r = st.q, st.G, slab.rank
+    dev = V.device
+    ent = {"setup": st, "q": q, "local_lu": BandLU.from_band(st.local_bands[r], dev)}
+    # rows of Sinv this rank needs: bot_{r-1} and top_{r+1}
+    rows = []
+    if r > 0:
+        rows += list(range(2 * q * (r - 1) + q, 2 * q * (r - 1) + 2 * q))
+    if r < G - 1:
+        rows += list(range(2 * q * (r + 1), 2 * q * (r + 1) + q))
+    if rows:
+        ent["reduce"] = _AxisOp(np.zeros(len(rows), dtype=np.int32), st.Sinv[rows], 2 * q * G, dev)
+    nl = table[r][1] - table[r][0] + 1
+    if r > 0 and st.mW[r] > 0:
+        m = st.mW[r]
+        ent["corrW"] = (_AxisOp(np.zeros(m, dtype=np.int32), -st.W[r][:m], q, dev), m)
+    if r < G - 1 and st.mV[r] > 0:
+        m = st.mV[r]
+        ent["corrV"] = (_AxisOp(np.zeros(m, dtype=np.int32), -st.V[r][nl - m:], q, dev), m)
+    _spike_cache[key] = ent
+    return ent
+
+
+def kron_solve_bnd_slab(factors, Y, X=None):
+    """X = (A_1 (x) .. (x) A_d)^-1 Y on a slab-partitioned space: SPIKE along axis 1, plain local
+    line solves along the other axes (kron_product.kron_solve_bnd is the one-GPU version)."""
+    from .kron_product import _solve_axis, BandLU
+    from .stencil import StencilVector
+    from . import profiling
+    V = Y.space
+    slab = V.slab
+    if X is None:
+        X = StencilVector(V)
+    lus = list(factors)
+    for f in lus:
+        if not isinstance(f, BandLU):
+            raise NotImplementedError("slab-partitioned solve takes BandLU factors")
+    sp = _spike_for(lus[0], V)
+    q = sp["q"]
+    shape = tuple(V.local_shape)
+    n1 = shape[0]
+    ld = V.ld
+    # 1. local diagonal-block solves along axis 1
+    with profiling.region("band_solve_axis1", 16 * V.local_size):
+        _solve_axis(sp["local_lu"], Y, X, 0)
+    if slab.size > 1:
+        with profiling.region("spike_interface", 0, launches=3):
+            # 2. interface planes of every slab -> everyone
+            zl = torch.cat([X.flat[:q], X.flat[n1 - q:]], dim=0).contiguous()
+            zt = torch.empty((2 * q * slab.size,) + tuple(zl.shape[1:]), dtype=zl.dtype,
+                             device=zl.device)
+            dist.all_gather_into_tensor(zt, zl, group=slab.group)
+            # 3. the rows of the reduced solution this slab needs
+            if "reduce" in sp:
+                op = sp["reduce"]
+                z = torch.empty((op.n_out,) + tuple(zl.shape[1:]), dtype=zl.dtype, device=zl.device)
+                op.apply(zt, z, (2 * q * slab.size,) + shape[1:], ld, ld, 0)
+                k = 0
+                # 4. truncated spike corrections near the two interfaces
+                if slab.rank > 0:
+                    zprev = z[k:k + q]
+                    k += q
+                    if "corrW" in sp:
+                        cop, m = sp["corrW"]
+                        cop.apply(zprev, X.flat[:m], (q,) + shape[1:], ld, ld, 0, accumulate=True)
+                if slab.rank < slab.size - 1:
+                    znext = z[k:k + q]
+                    if "corrV" in sp:
+                        cop, m = sp["corrV"]
+                        cop.apply(znext, X.flat[n1 - m:], (q,) + shape[1:], ld, ld, 0,
+                                  accumulate=True)
+    src = X
+    for ax in range(1, len(lus)):
+        with profiling.region("band_solve_axis%d" % (ax + 1), 16 * V.local_size):
+            _solve_axis(lus[ax], src, X, ax)
+    return X

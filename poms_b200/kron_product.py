@@ -67,6 +67,7 @@ class BandLU:
         # dgbtrf made no row interchange (SPD / diagonally dominant bands): the streaming
         # no-pivot kernels apply
         self.nopiv = bool(np.array_equal(np.asarray(piv), np.arange(self.n)))
+        self.band = None
 
     @property
     def piv_ptr(self):
@@ -80,7 +81,9 @@ class BandLU:
         q = p
         while q > 0 and not band[:, p - q].any() and not band[:, p + q].any():
             q -= 1
-        return cls(*bs.band_lu(band[:, p - q:p + q + 1]), device)
+        lu = cls(*bs.band_lu(band[:, p - q:p + q + 1]), device)
+        lu.band = band          # kept for the slab-partitioned (SPIKE) solve, dist.py
+        return lu
 
 
 def _solve_axis(lu, src, dst, axis):

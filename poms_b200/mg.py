@@ -31,7 +31,7 @@ from .stencil import (StencilVectorSpace, StencilVector, KronSumMatrix, DeviceCo
 from .kron_product import BandLU, kron_solve_bnd
 from . import solvers
 
-__all__ = ["Transfer", "CoarseSolver", "two_grid", "Hierarchy", "vcycle", "mg_pcg",
+__all__ = ["Transfer", "DistTransfer", "CoarseSolver", "two_grid", "Hierarchy", "vcycle", "mg_pcg",
            "fine_knots"]
 
 
@@ -115,7 +115,7 @@ class Transfer:
     def restrict(self, rf, Vc):
         """r_c = (P1^T (x) .. (x) P1^T) r_f.  Axis 1 first: the largest array is read once,
         fully coalesced, and every later pass works on a smaller one."""
-        assert rf.space.slab is None or rf.space.slab.size == 1, "use dist.restrict for slabs"
+        assert rf.space.slab is None or rf.space.slab.size == 1, "use DistTransfer for slabs"
         rc = StencilVector(Vc)
         cur, ld = rf.flat, rf.ld
         shape = tuple(rf.space.local_shape)
@@ -156,6 +156,85 @@ class Transfer:
                 assert ld_out == xf.ld
             shape = op.apply(cur, dst, shape, ld, ld_out, ax, accumulate=last)
             cur, ld = dst, ld_out
+        return xf
+
+
+class DistTransfer(Transfer):
+    """Transfer whose FINE space is slab-partitioned along axis 1.  The coarse space is either
+    partitioned too, or replicated on every rank (the level where the hierarchy is gathered: the
+    analogue of `rc = comm.allreduce(rc)`, /root/reference/sources/mg_jac.py:95).
+
+    Axis-1 passes work on plane blocks: the few fine (restriction) or coarse (prolongation) planes
+    that belong to a neighbour are fetched with one send/recv pair; axes 2..d are local."""
+
+    def __init__(self, Tc_axes, Tf_axes, p, device, slab, coarse_distributed):
+        from .dist import slab_transfer_plan
+        super().__init__(Tc_axes, Tf_axes, p, device)
+        self.slab = slab
+        self.cdist = coarse_distributed
+        assert self.P[0] is not None, "the partitioned axis must be refined between levels"
+        st, cf, nc = self.P1_rows[0]
+        plan = slab_transfer_plan(st, cf, nc, slab.size, coarse_distributed)
+        r = slab.rank
+        self.tf, self.tc = plan["tf"], plan["tc"]
+        self.need_f, self.need_c = plan["need_f"], plan["need_c"]
+        self.R0 = _AxisOp(plan["R0"][r][0], plan["R0"][r][1], plan["R0"][r][2], device)
+        self.P0 = _AxisOp(plan["P0"][r][0], plan["P0"][r][1], plan["P0"][r][2], device)
+
+    def restrict(self, rf, Vc):
+        slab = self.slab
+        nd = len(rf.space.local_shape)
+        ld = rf.ld
+        planes = slab.gather_planes(rf.flat, self.tf, self.need_f)
+        shape = (planes.shape[0],) + tuple(rf.space.local_shape[1:])
+        cs, ce = self.tc[slab.rank]
+        ops = [(ax, op) for ax, op in enumerate(self.R) if op is not None and ax > 0]
+        rc = StencilVector(Vc)
+        own_view = rc.flat if self.cdist else None
+        # axis 1 (slab axis)
+        last = not ops
+        if last and self.cdist:
+            dst = own_view
+        else:
+            dst = _tmp((ce - cs + 1,) + shape[1:], ld, self.device, zero=False)
+        shape = self.R0.apply(planes, dst, shape, ld, ld, 0)
+        cur = dst
+        for n, (ax, op) in enumerate(ops):
+            shape_out = list(shape)
+            shape_out[ax] = op.n_out
+            last = n == len(ops) - 1
+            ld_out = _pitch(op.n_out) if ax == nd - 1 else ld
+            if last and self.cdist:
+                dst = own_view
+            else:
+                dst = _tmp(shape_out, ld_out, self.device, zero=(ax == nd - 1))
+            shape = op.apply(cur, dst, shape, ld, ld_out, ax)
+            cur, ld = dst, ld_out
+        if not self.cdist:
+            full = slab.allgather_planes(cur, self.tc)
+            rc.flat.copy_(full)
+        return rc
+
+    def prolong_add(self, ec, xf):
+        slab = self.slab
+        cur, ld = ec.flat, ec.ld
+        shape = tuple(ec.space.local_shape)
+        nd = len(shape)
+        ops = [(ax, op) for ax, op in reversed(list(enumerate(self.P))) if op is not None and ax > 0]
+        for ax, op in ops:
+            shape_out = list(shape)
+            shape_out[ax] = op.n_out
+            ld_out = _pitch(op.n_out) if ax == nd - 1 else ld
+            dst = _tmp(shape_out, ld_out, self.device, zero=(ax == nd - 1))
+            shape = op.apply(cur, dst, shape, ld, ld_out, ax)
+            cur, ld = dst, ld_out
+        assert ld == xf.ld
+        if self.cdist:
+            planes = slab.gather_planes(cur, self.tc, self.need_c)
+        else:
+            planes = cur
+        shape = (planes.shape[0],) + tuple(shape[1:])
+        self.P0.apply(planes, xf.flat, shape, ld, ld, 0, accumulate=True)
         return xf
 
 
@@ -291,9 +370,15 @@ class Hierarchy:
             lv.N = list(Ns)
             lv.knots = [bs.make_open_knots(p, n + p) for n in Ns]
             lv.A = KronSumMatrix.poisson(p, lv.knots)
+            # a level stays slab-partitioned while every slab keeps enough planes for the p-wide
+            # halo and the 2q interface planes of the partitioned solve; below that it is gathered
+            # and every rank works on the whole (small) grid redundantly
+            lv.distributed = (slab is not None and slab.size > 1
+                              and (not self.levels or self.levels[-1].distributed)
+                              and (Ns[0] + p) >= slab.size * max(2 * p + 2, 8))
             lv.V = StencilVectorSpace([n + p for n in Ns], [p] * self.ndim,
                                       [False] * self.ndim, device=self.device,
-                                      slab=slab if not self.levels else None)
+                                      slab=slab if lv.distributed else None)
             self.levels.append(lv)
             if all(n <= Nc for n in Ns):
                 break
@@ -302,7 +387,13 @@ class Hierarchy:
                 break
             Ns = nxt
         for f, c in zip(self.levels[:-1], self.levels[1:]):
-            f.transfer = Transfer(c.knots, f.knots, p, self.device)
+            if f.distributed:
+                f.transfer = DistTransfer(c.knots, f.knots, p, self.device, slab, c.distributed)
+            else:
+                f.transfer = Transfer(c.knots, f.knots, p, self.device)
+        if slab is not None and slab.size > 1 and self.levels[-1].distributed:
+            raise NotImplementedError("the coarsest level must be replicated: use a larger Nc "
+                                      "or fewer ranks")
         self.coarse = CoarseSolver(self.levels[-1].A, self.device)
         for lv in self.levels[:-1]:
             self._setup_smoother(lv)

@@ -1,0 +1,115 @@
+"""Multi-rank host logic on CPU: world_size-2 (and 3) gloo process groups exercise the slab
+partition, the halo exchange, the neighbour plane gathers of the grid transfer, the all-gather of
+the gathered level and the scalar all-reduce with CPU tensors; the SPIKE partitioned banded solve
+is checked against a dense solve.  (The CUDA kernels themselves are covered by -m gpu tests.)"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from poms_b200 import bsplines as bs
+from poms_b200.dist import (Slab, block_bounds, SpikeSetup, spike_solve_host, slab_transfer_plan)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _rows_apply(start, coef, X):
+    out = np.zeros((coef.shape[0],) + X.shape[1:])
+    for w in range(coef.shape[1]):
+        j = start + w
+        ok = (j >= 0) & (j < X.shape[0]) & (coef[:, w] != 0.0)
+        out[ok] += coef[ok, w][:, None] * X[j[ok]]
+    return out
+
+
+def _worker(rank, world, port, p, N, coarse_distributed):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        slab = Slab(dist.group.WORLD, torch.device("cpu"))
+        assert slab.rank == rank and slab.size == world
+        rng = np.random.default_rng(42)
+        nf, nc, m = N + p, N // 2 + p, 5
+        # ---- partition covers the range exactly once
+        tab = slab.table(nf)
+        assert tab[0][0] == 0 and tab[-1][1] == nf - 1
+        assert all(tab[i][1] + 1 == tab[i + 1][0] for i in range(world - 1))
+        # ---- halo exchange of p planes
+        Xg = rng.standard_normal((nf, m))
+        s, e = tab[rank]
+        glo = p if rank > 0 else 0
+        ghi = p if rank < world - 1 else 0
+        buf = torch.zeros((glo + e - s + 1 + ghi, m), dtype=torch.float64)
+        buf[glo:glo + e - s + 1] = torch.from_numpy(Xg[s:e + 1])
+        slab.exchange_planes(buf, e - s + 1, glo, ghi, p)
+        assert np.array_equal(buf.numpy(), Xg[s - glo:e + 1 + ghi])
+        # ---- all-reduce of a scalar (StencilVector.dot)
+        t = torch.tensor([float(np.dot(Xg[s:e + 1, 0], Xg[s:e + 1, 1]))], dtype=torch.float64)
+        slab.allreduce_sum(t)
+        assert abs(t.item() - np.dot(Xg[:, 0], Xg[:, 1])) < 1e-12
+        # ---- grid transfer along the partitioned axis
+        Tf, Tc = bs.make_open_knots(p, nf), bs.make_open_knots(p, nc)
+        st, cf, _ = bs.knot_insertion_rows(Tc, Tf, p)
+        P1 = bs.rows_to_dense(st, cf, nc)
+        plan = slab_transfer_plan(st, cf, nc, world, coarse_distributed)
+        tf, tc = plan["tf"], plan["tc"]
+        assert tf == tab
+        own_f = torch.from_numpy(np.ascontiguousarray(Xg[s:e + 1]))
+        planes = slab.gather_planes(own_f, tf, plan["need_f"]).numpy()
+        lo, hi = plan["need_f"][rank]
+        assert np.array_equal(planes, Xg[lo:hi + 1])
+        r0s, r0c, r0n = plan["R0"][rank]
+        assert r0n == hi - lo + 1
+        rc_own = _rows_apply(r0s, r0c, planes)
+        rc_ref = P1.T @ Xg
+        cs, ce = tc[rank]
+        assert np.abs(rc_own - rc_ref[cs:ce + 1]).max() < 1e-13
+        # gathered (replicated) coarse level
+        full = slab.allgather_planes(torch.from_numpy(rc_own), tc).numpy()
+        assert np.abs(full - rc_ref).max() < 1e-13
+        # prolongation
+        Eg = rng.standard_normal((nc, m))
+        p0s, p0c, p0n = plan["P0"][rank]
+        if coarse_distributed:
+            own_c = torch.from_numpy(np.ascontiguousarray(Eg[cs:ce + 1]))
+            cplanes = slab.gather_planes(own_c, tc, plan["need_c"]).numpy()
+            clo, chi = plan["need_c"][rank]
+            assert np.array_equal(cplanes, Eg[clo:chi + 1]) and p0n == chi - clo + 1
+        else:
+            cplanes = Eg
+        xf_own = _rows_apply(p0s, p0c, cplanes)
+        assert np.abs(xf_own - (P1 @ Eg)[s:e + 1]).max() < 1e-13
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,p,N,cdist", [(2, 3, 32, True), (2, 3, 32, False), (3, 2, 48, True),
+                                              (2, 5, 64, True), (2, 1, 16, False)])
+def test_slab_plumbing_gloo(world, p, N, cdist):
+    mp.spawn(_worker, args=(world, _free_port(), p, N, cdist), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("p,q,n,G", [(3, 5, 131, 4), (3, 3, 67, 2), (2, 3, 45, 3), (5, 9, 260, 8),
+                                      (1, 1, 40, 2)])
+def test_spike_partitioned_solve(p, q, n, G):
+    band = bs.glt_band(p, n, degree=q) if q != p else bs.assemble_1d_bands(
+        p, bs.make_open_knots(p, n))[0]
+    table = [block_bounds(n, G, r) for r in range(G)]
+    st = SpikeSetup(band, table)
+    y = np.random.default_rng(0).standard_normal((n, 4))
+    x = np.concatenate(spike_solve_host(st, [y[s:e + 1] for s, e in table]))
+    xr = np.linalg.solve(bs.band_to_dense(band), y)
+    assert np.abs(x - xr).max() < 1e-13 * np.abs(xr).max()
+    # truncated spikes: the correction only touches planes near the interfaces
+    assert max(st.mW) <= 60 and max(st.mV) <= 60
