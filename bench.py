@@ -180,7 +180,11 @@ def main():
     Ns = [N] * ndim
     if world > 1:
         Ns[0] = N * world          # weak scaling: N element planes per GPU along axis 1
-    h = Hierarchy(p, Ns, device=dev, smoother=args.smoother, nu=args.nu, slab=slab)
+    # weak scaling: the domain grows with the grid, [0, G] x [0,1]^(d-1), so the elements stay cubes
+    # (keeping [0,1]^d would make the global problem anisotropic and change the iteration count)
+    lengths = [float(world)] + [1.0] * (ndim - 1)
+    h = Hierarchy(p, Ns, device=dev, smoother=args.smoother, nu=args.nu, slab=slab,
+                  lengths=lengths)
     V = h.levels[0].V
     dof_global = int(np.prod(V.npts))
     b = StencilVector(V)
@@ -279,7 +283,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc + (" per GPU, slab-partitioned along axis 1" if world > 1
                                        else ""),
-                   "ndim": ndim, "p": p, "elements": Ns, "dof": dof_global,
+                   "ndim": ndim, "p": p, "elements": Ns, "dof": dof_global, "domain": lengths,
                    "solver": "pcg + V(%d,%d) %s-Chebyshev multigrid, tol 1e-10 relative"
                              % (args.nu, args.nu, args.smoother),
                    "iterations": info["niter"], "levels": len(h.levels),

@@ -559,14 +559,15 @@ def pcg_relative(A, psolve, b, x0=None, tol=1e-10, maxiter=200, log=None):
 
 
 class MGHierarchy:
-    def __init__(self, p, N, Nc=8, smoother="glt", nu=1, ratio=4.0, safety=1.1):
+    def __init__(self, p, N, Nc=8, smoother="glt", nu=1, ratio=4.0, safety=1.1, lengths=None):
         from scipy.linalg import eigh
+        lengths = [1.0] * len(N) if lengths is None else [float(v) for v in lengths]
         self.p, self.smoother, self.nu, self.ratio = p, smoother, nu, ratio
         N = list(N)
         d = len(N)
         self.levels = []
         while True:
-            knots = [make_open_knots(p, n + p) for n in N]
+            knots = [make_open_knots(p, n + p) * L for n, L in zip(N, lengths)]
             A, Mb, Kb = poisson_operator(p, knots)
             self.levels.append(dict(N=list(N), knots=knots, A=A, Mb=Mb, Kb=Kb))
             if all(n <= Nc for n in N):

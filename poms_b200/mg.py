@@ -357,9 +357,12 @@ class Hierarchy:
     """
 
     def __init__(self, p, N, ndim=None, Nc=8, device="cuda", smoother="glt", nu=1, ratio=4.0,
-                 safety=1.1, slab=None):
+                 safety=1.1, slab=None, lengths=None):
         if np.isscalar(N):
             N = [int(N)] * int(ndim)
+        # domain [0, L_1] x .. x [0, L_d] (default the unit cube).  Weak scaling extends the domain
+        # along the slab axis (L_1 = number of GPUs) so that the elements stay cubes.
+        self.lengths = [1.0] * len(N) if lengths is None else [float(v) for v in lengths]
         self.p, self.ndim = p, len(N)
         self.device = torch.device(device)
         self.smoother, self.nu, self.ratio, self.safety = smoother, nu, ratio, safety
@@ -368,7 +371,7 @@ class Hierarchy:
         while True:
             lv = Level()
             lv.N = list(Ns)
-            lv.knots = [bs.make_open_knots(p, n + p) for n in Ns]
+            lv.knots = [bs.make_open_knots(p, n + p) * L for n, L in zip(Ns, self.lengths)]
             lv.A = KronSumMatrix.poisson(p, lv.knots)
             # a level stays slab-partitioned while every slab keeps enough planes for the p-wide
             # halo and the 2q interface planes of the partitioned solve; below that it is gathered

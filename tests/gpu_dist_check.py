@@ -58,8 +58,10 @@ for (p, N) in ((3, (32 * world, 16, 24)), (2, (64, 40)), (3, (64 * world, 32))):
     err = np.abs(z.data.cpu().numpy() - Zo[s:e + 1]).max() / np.abs(Zo).max()
     check("kron solve (SPIKE) %dD p=%d" % (d, p), err < 1e-12, "%.1e" % err)
     # MG-PCG: identical iteration count and history vs the oracle
-    h = Hierarchy(p, list(N), device=dev, slab=slab)
-    ho = po.MGHierarchy(p, list(N))
+    # isotropic weak-scaling geometry: the domain is as many units long as the grid is wide
+    lengths = [n / min(N) for n in N]
+    h = Hierarchy(p, list(N), device=dev, slab=slab, lengths=lengths)
+    ho = po.MGHierarchy(p, list(N), lengths=lengths)
     bb = StencilVector(h.levels[0].V)
     bb.data.fill_(1.0)
     xs, info = mg_pcg(h, bb, tol=1e-10, maxiter=100)
