@@ -81,6 +81,9 @@ int poms_kron_matvec_3d_ex(const double* x, double* y, const double* b,
                            int epilogue, double omega, double* dot_out, void* ws, void* stream,
                            const double* toep_host, const int* toep_rng_host);
 void poms_set_force_generic(int flag);
+/* 3-D TMA kernel variant: 0 = block-synchronous (default; 1.51 ms at 512^3), 1 = warp-private strips
+ * (1.64 ms; kept for A-B timing) */
+void poms_set_matvec3d_variant(int v);
 
 /*
  * Full (non-separable) 2-D stencil mat-vec: y[i1,i2] = sum_{k1,k2} S[i1,i2,k1,k2] x[i1+k1-p1,i2+k2-p2]

@@ -1048,10 +1048,16 @@ __global__ void __launch_bounds__(128) band_solve_cols_nopiv_kernel(
     double z[KL > 0 ? KL : 1];
 #pragma unroll
     for (int m = 0; m < KL; ++m) z[m] = 0.0;  // z[m-1] = z_{j-m}
-    for (int j0 = 0; j0 < n; j0 += UNR) {
-        double v[UNR];
+    double v[UNR], vn[UNR];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) v[u] = (j0 + u < n) ? yl[(int64_t)(j0 + u) * s_axis] : 0.0;
+    for (int u = 0; u < UNR; ++u) vn[u] = (u < n) ? yl[(int64_t)u * s_axis] : 0.0;
+    for (int j0 = 0; j0 < n; j0 += UNR) {
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) v[u] = vn[u];
+        // prefetch the next batch while this one is processed
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+            vn[u] = (j0 + UNR + u < n) ? yl[(int64_t)(j0 + UNR + u) * s_axis] : 0.0;
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int j = j0 + u;
@@ -1071,14 +1077,22 @@ __global__ void __launch_bounds__(128) band_solve_cols_nopiv_kernel(
 #pragma unroll
     for (int m = 0; m < KU; ++m) w[m] = 0.0;  // w[m-1] = x_{j+m}
     const int nb = (n + UNR - 1) / UNR;
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+        const int j = (nb - 1) * UNR + u;
+        vn[u] = (j < n) ? xl[(int64_t)j * s_axis] : 0.0;
+    }
     for (int b = nb - 1; b >= 0; --b) {
         const int j0 = b * UNR;
-        double v[UNR], rd[UNR];
+        double rd[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            const bool ok = j0 + u < n;
-            v[u] = ok ? xl[(int64_t)(j0 + u) * s_axis] : 0.0;
-            rd[u] = ok ? 1.0 / __ldg(ab + (int64_t)KD * n + (j0 + u)) : 0.0;
+            v[u] = vn[u];
+            rd[u] = (j0 + u < n) ? 1.0 / __ldg(ab + (int64_t)KD * n + (j0 + u)) : 0.0;
+        }
+        if (b > 0) {
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) vn[u] = xl[(int64_t)(j0 - UNR + u) * s_axis];
         }
 #pragma unroll
         for (int u = UNR - 1; u >= 0; --u) {
@@ -1146,17 +1160,28 @@ __global__ void __launch_bounds__(32 * BSR_WARPS) band_solve_rows_nopiv_kernel(
         const int jend = min(32, n - t * 32);
         if (mine) {
             double* row = cur + lane * BSR_PITCH;
-#pragma unroll 4
-            for (int u = 0; u < jend; ++u) {
-                const int j = t * 32 + u;
-                double s = row[u];
+            for (int u0 = 0; u0 < jend; u0 += 8) {
+                double c[8];
 #pragma unroll
-                for (int m = KL; m >= 1; --m)
-                    if (j - m >= 0) s = fma(-__ldg(ab + (int64_t)(KD + m) * n + (j - m)), z[m - 1], s);
-                row[u] = s;
+                for (int q = 0; q < 8; ++q) c[q] = row[min(u0 + q, 31)];
 #pragma unroll
-                for (int m = KL - 1; m >= 1; --m) z[m] = z[m - 1];
-                if (KL > 0) z[0] = s;
+                for (int q = 0; q < 8; ++q) {
+                    const int j = t * 32 + u0 + q;
+                    if (u0 + q < jend) {
+                        double s = c[q];
+#pragma unroll
+                        for (int m = KL; m >= 1; --m)
+                            if (j - m >= 0)
+                                s = fma(-__ldg(ab + (int64_t)(KD + m) * n + (j - m)), z[m - 1], s);
+                        c[q] = s;
+#pragma unroll
+                        for (int m = KL - 1; m >= 1; --m) z[m] = z[m - 1];
+                        if (KL > 0) z[0] = s;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (u0 + q < jend) row[u0 + q] = c[q];
             }
         }
         __syncwarp();
@@ -1180,19 +1205,33 @@ __global__ void __launch_bounds__(32 * BSR_WARPS) band_solve_rows_nopiv_kernel(
         const int jend = min(32, n - t * 32);
         if (mine) {
             double* row = cur + lane * BSR_PITCH;
-#pragma unroll 4
-            for (int u = jend - 1; u >= 0; --u) {
-                const int j = t * 32 + u;
-                double s = row[u];
-                const double rd = 1.0 / __ldg(ab + (int64_t)KD * n + j);
+            for (int u0 = 24; u0 >= 0; u0 -= 8) {
+                if (u0 >= jend) continue;
+                double c[8], rd[8];
 #pragma unroll
-                for (int m = KU; m >= 1; --m)
-                    if (j + m < n) s = fma(-__ldg(ab + (int64_t)(KD - m) * n + (j + m)), w[m - 1], s);
-                s *= rd;
-                row[u] = s;
+                for (int q = 0; q < 8; ++q) {
+                    c[q] = row[u0 + q];
+                    rd[q] = 1.0 / __ldg(ab + (int64_t)KD * n + min(t * 32 + u0 + q, n - 1));
+                }
 #pragma unroll
-                for (int m = KU - 1; m >= 1; --m) w[m] = w[m - 1];
-                if (KU > 0) w[0] = s;
+                for (int q = 7; q >= 0; --q) {
+                    const int j = t * 32 + u0 + q;
+                    if (u0 + q < jend) {
+                        double s = c[q];
+#pragma unroll
+                        for (int m = KU; m >= 1; --m)
+                            if (j + m < n)
+                                s = fma(-__ldg(ab + (int64_t)(KD - m) * n + (j + m)), w[m - 1], s);
+                        s *= rd[q];
+                        c[q] = s;
+#pragma unroll
+                        for (int m = KU - 1; m >= 1; --m) w[m] = w[m - 1];
+                        if (KU > 0) w[0] = s;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (u0 + q < jend) row[u0 + q] = c[q];
             }
         }
         __syncwarp();
@@ -1300,12 +1339,64 @@ __global__ void __launch_bounds__(256) axis_gather_kernel(
     }
 }
 
+// Fast path for passes along a NON-contiguous axis: one output row per blockIdx.y, lanes on the
+// contiguous index with 128-bit loads/stores, the W coefficients of the row are block-uniform.
+template <int ACC>
+__global__ void __launch_bounds__(256) axis_gather_strided2_kernel(
+    const double2* __restrict__ in, double2* __restrict__ out, const int32_t* __restrict__ start,
+    const double* __restrict__ coef, int W, int n_in, int n_out, int64_t so_in2, int64_t sa_in2,
+    int64_t so_out2, int64_t sa_out2, int64_t n_inner2) {
+    const int i = blockIdx.y;
+    const int64_t o = blockIdx.z;
+    const int s0 = __ldg(start + i);
+    const double* cf = coef + (int64_t)i * W;
+    const double2* ip = in + o * so_in2;
+    double2* op = out + o * so_out2 + (int64_t)i * sa_out2;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_inner2;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        for (int w = 0; w < W; ++w) {
+            const int j = s0 + w;
+            if (j >= 0 && j < n_in) {
+                const double cw = __ldg(cf + w);
+                const double2 x = ip[(int64_t)j * sa_in2 + c];
+                v.x = fma(cw, x.x, v.x);
+                v.y = fma(cw, x.y, v.y);
+            }
+        }
+        if (ACC) {
+            const double2 old = op[c];
+            v.x += old.x;
+            v.y += old.y;
+        }
+        op[c] = v;
+    }
+}
+
 extern "C" int poms_axis_gather(const double* in, double* out, const int32_t* start,
                                 const double* coef, int W, int n_in, int n_out, int64_t n_outer,
                                 int64_t so_in, int64_t sa_in, int64_t so_out, int64_t sa_out,
                                 int64_t n_inner, int accumulate, void* stream) {
     if (!in || !out || !start || !coef) return bad_arg(1, "null pointer");
     if (W < 1 || n_in < 1 || n_out < 1 || n_outer < 1 || n_inner < 1) return bad_arg(5, "extent");
+    const bool even = !((n_inner | so_in | sa_in | so_out | sa_out) & 1) &&
+                      !(((uintptr_t)in | (uintptr_t)out) & 15);
+    if (even && n_inner >= 64 && n_out <= 65535 && n_outer <= 65535) {
+        const int64_t n2 = n_inner / 2;
+        int gx = (int)((n2 + 511) / 512);   // ~2 double2 per thread
+        if (gx < 1) gx = 1;
+        dim3 grid(gx, n_out, (unsigned)n_outer);
+        if (accumulate)
+            axis_gather_strided2_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                (const double2*)in, (double2*)out, start, coef, W, n_in, n_out, so_in / 2, sa_in / 2,
+                so_out / 2, sa_out / 2, n2);
+        else
+            axis_gather_strided2_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                (const double2*)in, (double2*)out, start, coef, W, n_in, n_out, so_in / 2, sa_in / 2,
+                so_out / 2, sa_out / 2, n2);
+        CHECK_LAUNCH("poms_axis_gather(strided2)");
+        return 0;
+    }
     const int64_t total = n_outer * n_out * n_inner;
     int64_t g = (total + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;

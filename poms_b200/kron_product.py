@@ -116,7 +116,7 @@ def kron_solve_bnd(factors, Y, X=None):
     lus = [f if isinstance(f, BandLU) else BandLU(f[0], f[1], f[2], f[3], V.device)
            for f in factors]
     if X is None:
-        X = StencilVector(V)
+        X = StencilVector(V, zero=False)
     src = Y
     for ax, lu in enumerate(lus):
         # algorithmic bytes of one dgbtrs sweep pair: forward (read y, write t) + backward

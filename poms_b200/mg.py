@@ -452,9 +452,9 @@ class Hierarchy:
         delta = 0.5 * (lv.lmax - lv.lmin)
         sigma = theta / delta
         rho = 1.0 / sigma
-        r = StencilVector(V)
-        z = StencilVector(V) if self.smoother == "glt" else r
-        d = StencilVector(V)
+        r = StencilVector(V, zero=False)
+        z = StencilVector(V, zero=False) if self.smoother == "glt" else r
+        d = StencilVector(V, zero=False)      # written (c1 = 0) by the first Chebyshev step
         for k in range(self.nu):
             if self.smoother == "glt":
                 if k == 0 and zero_guess:
@@ -487,7 +487,7 @@ def vcycle(h, l, b):
         return h.coarse.solve(b)
     x = StencilVector(lv.V)
     h.smooth(lv, b, x, True)
-    r = StencilVector(lv.V)
+    r = StencilVector(lv.V, zero=False)
     lv.A.apply(x, r, EPI_RESID, b=b)
     with profiling.region("restrict", 8 * lv.V.local_size, launches=h.ndim):
         rc = lv.transfer.restrict(r, h.levels[l + 1].V)

@@ -56,7 +56,7 @@ def _residual(A, b, x0, ctx):
         dot_into(r, r, ctx.sptr(S_RR), ctx)
     else:
         x = x0.copy()
-        r = StencilVector(V)
+        r = StencilVector(V, zero=False)
         A.apply(x, r, EPI_RESID, b=b, dot_ptr=ctx.sptr(S_RR))
     return x, r
 
@@ -76,7 +76,7 @@ def _pcg_driver(A, psolve, b, x0, tol, maxiter, verbose, title, relative=False):
     cur = S_SR0
     dot_into(s, r, ctx.sptr(cur), ctx)
     _reduce(ctx, V, cur)
-    q = StencilVector(V)
+    q = StencilVector(V, zero=False)
     if verbose:
         print(title)
         print("+---------+---------------------+")
@@ -139,7 +139,7 @@ def pcg_glt(A, M1, M2, b, x0=None, tol=1e-6, maxiter=100, verbose=False):
 def jacobi(A, b):
     """x = b / diag(A) (/root/reference/sources/solvers.py:139-163)."""
     _check_shapes(A, b, None)
-    x = StencilVector(b.space)
+    x = StencilVector(b.space, zero=False)
     A.jacobi_first(x, b, 1.0, None)
     return x
 
@@ -158,14 +158,14 @@ def damped_jacobi(A, b, x0=None, tol=1e-6, maxiter=10, verbose=False, omega=2.0 
         if maxiter < 1:
             return StencilVector(V)
         # sweep 1 from x = 0: r = b - A.0 = b, so x = omega*b/diag (one 16 B/DOF pass)
-        x = StencilVector(V)
+        x = StencilVector(V, zero=False)
         A.jacobi_first(x, b, omega, ctx.sptr(S_DR))
         if _read(ctx, V, S_DR) < tol_sqr:
             return x
         first = 2
     else:
         x = x0.copy()
-    y = StencilVector(V)
+    y = StencilVector(V, zero=False)
     for k in range(first, maxiter + 1):
         # one fused pass: y = x + omega*(b - A x)/diag ; dr.dr   (lines 209-219)
         A.apply(x, y, EPI_JACOBI, b=b, omega=omega, dot_ptr=ctx.sptr(S_DR))

@@ -142,11 +142,22 @@ class StencilVectorSpace:
 
 
 class StencilVector:
-    def __init__(self, V, _buf=None):
+    def __init__(self, V, _buf=None, zero=True):
+        """zero=False: storage is left uninitialised except for the pad column and the ghost
+        planes (for vectors that a kernel overwrites completely; saves a full-size memset)."""
         self._space = V
         shape = (V.glo + V.local_shape[0] + V.ghi,) + V.pitched_shape[1:]
         if _buf is None:
-            _buf = torch.zeros(shape, dtype=torch.float64, device=V.device)
+            if zero:
+                _buf = torch.zeros(shape, dtype=torch.float64, device=V.device)
+            else:
+                _buf = torch.empty(shape, dtype=torch.float64, device=V.device)
+                if V.ld != V.local_shape[-1]:
+                    _buf[..., V.local_shape[-1]:] = 0.0
+                if V.glo:
+                    _buf[:V.glo] = 0.0
+                if V.ghi:
+                    _buf[V.glo + V.local_shape[0]:] = 0.0
         assert tuple(_buf.shape) == shape and _buf.is_contiguous()
         self._buf = _buf
         self.flat = _buf[V.glo:V.glo + V.local_shape[0]]          # owned planes, pitched
@@ -197,7 +208,7 @@ class StencilVector:
         self._buf[self._local(key)] = value
 
     def copy(self):
-        w = StencilVector(self._space)
+        w = StencilVector(self._space, _buf=torch.empty_like(self._buf))
         w._buf.copy_(self._buf)
         return w
 
@@ -224,7 +235,7 @@ class StencilVector:
             self._space.slab.exchange(self)
 
     def _axpby(self, a, b, y):
-        z = StencilVector(self._space)
+        z = StencilVector(self._space, zero=False)
         L = _lib.lib()
         _lib.check(L.poms_axpby(z.ptr, float(a), self.ptr, float(b),
                                  y.ptr if y is not None else None, self.n_owned, _stream()),
@@ -563,7 +574,7 @@ class KronSumMatrix:
                 "poms_kron_matvec_3d_ex")
 
     def dot(self, v):
-        out = StencilVector(v.space)
+        out = StencilVector(v.space, zero=False)
         self.apply(v, out)
         return out
 
