@@ -146,6 +146,17 @@ int poms_band_solve_axis(const double* y, double* x, const double* ab, const int
                          int64_t n_inner, void* stream);
 
 /*
+ * No-pivot banded solve along the CONTIGUOUS axis with a fused epilogue:
+ *   out = [add +] scale * T^-1 y      (work receives the forward-substitution intermediate)
+ * EXTENSION used by the multi-level smoother: the Chebyshev / Richardson update
+ * x += (1/theta) B^-1 r is folded into the last line solve of the Kronecker solve, so the
+ * correction is never written to and re-read from HBM.  n_lines lines, s_line doubles apart.
+ */
+int poms_band_solve_axis_fused(const double* y, double* work, const double* ab, int n, int kl,
+                               int ku, int64_t n_lines, int64_t s_line, double scale,
+                               const double* add, double* out, void* stream);
+
+/*
  * Per-axis sparse row-gather: out[o, i, c] (+)= sum_{w<W} coef[i*W+w] * in[o, start[i]+w, c].
  * With the rows of P1 it is the prolongation, with the rows of P1^T the restriction of
  * sources/mg_jac.py:67-70,94,102 applied one axis at a time (knot-insertion transfer).

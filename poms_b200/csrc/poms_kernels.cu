@@ -1120,7 +1120,7 @@ __global__ void __launch_bounds__(128) band_solve_cols_nopiv_kernel(
 template <int KL, int KU>
 __global__ void __launch_bounds__(32 * BSR_WARPS) band_solve_rows_nopiv_kernel(
     const double* __restrict__ y, double* __restrict__ x, const double* __restrict__ ab, int n,
-    int64_t n_lines, int64_t s_line) {
+    int64_t n_lines, int64_t s_line, double scale, const double* add, double* out) {
     constexpr int KD = KL + KU;
     extern __shared__ double smem_bsr[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1143,6 +1143,30 @@ __global__ void __launch_bounds__(32 * BSR_WARPS) band_solve_rows_nopiv_kernel(
         const int col = t * 32 + lane;
         if (col < n) {
             for (int r = 0; r < nl; ++r) x[(l0 + r) * s_line + col] = tile[r * BSR_PITCH + lane];
+        }
+    };
+    // final store of the backward sweep: out = [add +] scale * solution (fused smoother update)
+    auto store_final = [&](double* tile, int t) {
+        const int col = t * 32 + lane;
+        if (col < n) {
+            if (add) {
+                // batches of 8 rows: all loads first (add may alias out, so the compiler cannot
+                // hoist them across the stores itself)
+                for (int r0 = 0; r0 < nl; r0 += 8) {
+                    double a8[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        a8[q] = (r0 + q < nl) ? add[(l0 + r0 + q) * s_line + col] : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (r0 + q < nl)
+                            out[(l0 + r0 + q) * s_line + col] =
+                                __dadd_rn(a8[q], __dmul_rn(scale, tile[(r0 + q) * BSR_PITCH + lane]));
+                }
+            } else {
+                for (int r = 0; r < nl; ++r)
+                    out[(l0 + r) * s_line + col] = __dmul_rn(scale, tile[r * BSR_PITCH + lane]);
+            }
         }
     };
 
@@ -1235,7 +1259,7 @@ __global__ void __launch_bounds__(32 * BSR_WARPS) band_solve_rows_nopiv_kernel(
             }
         }
         __syncwarp();
-        store(cur, t);
+        store_final(cur, t);
         __syncwarp();
     }
     cp_async_wait<0>();
@@ -1244,8 +1268,11 @@ __global__ void __launch_bounds__(32 * BSR_WARPS) band_solve_rows_nopiv_kernel(
 template <int KL>
 static int band_solve_nopiv_ku(int ku, const double* y, double* x, const double* ab, int n,
                                int64_t n_outer, int64_t s_outer, int64_t s_axis, int64_t n_inner,
-                               cudaStream_t st) {
+                               cudaStream_t st, double scale = 1.0, const double* add = nullptr,
+                               double* out = nullptr) {
     const bool rows = (n_inner == 1 && s_axis == 1);
+    if (!out) out = x;
+    if (!rows && (add || out != x || scale != 1.0)) return bad_arg(13, "fused epilogue needs the contiguous axis");
     const int64_t lines = n_outer * n_inner;
     const size_t smem = (size_t)BSR_WARPS * 2 * 32 * BSR_PITCH * sizeof(double);
 #define BSN(KU_)                                                                                  \
@@ -1257,8 +1284,8 @@ static int band_solve_nopiv_ku(int ku, const double* y, double* x, const double*
             attr_set = true;                                                                      \
         }                                                                                         \
         const int grid = (int)((lines + 32 * BSR_WARPS - 1) / (32 * BSR_WARPS));                  \
-        band_solve_rows_nopiv_kernel<KL, KU_><<<grid, 32 * BSR_WARPS, smem, st>>>(y, x, ab, n,    \
-                                                                                  lines, s_outer); \
+        band_solve_rows_nopiv_kernel<KL, KU_><<<grid, 32 * BSR_WARPS, smem, st>>>(                \
+            y, x, ab, n, lines, s_outer, scale, add, out);                                        \
     } else {                                                                                      \
         const int grid = (int)((lines + 127) / 128);                                              \
         band_solve_cols_nopiv_kernel<KL, KU_><<<grid, 128, 0, st>>>(y, x, ab, n, n_outer,         \
@@ -1274,6 +1301,28 @@ static int band_solve_nopiv_ku(int ku, const double* y, double* x, const double*
         default: return bad_arg(7, "ku must be 0..5");
     }
 #undef BSN
+    return 0;
+}
+
+extern "C" int poms_band_solve_axis_fused(const double* y, double* work, const double* ab, int n,
+                                          int kl, int ku, int64_t n_lines, int64_t s_line,
+                                          double scale, const double* add, double* out,
+                                          void* stream) {
+    if (!y || !work || !ab || !out) return bad_arg(1, "null pointer");
+    if (n < 1 || n_lines < 1) return bad_arg(4, "extent");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    switch (kl) {
+        case 0: rc = band_solve_nopiv_ku<0>(ku, y, work, ab, n, n_lines, s_line, 1, 1, st, scale, add, out); break;
+        case 1: rc = band_solve_nopiv_ku<1>(ku, y, work, ab, n, n_lines, s_line, 1, 1, st, scale, add, out); break;
+        case 2: rc = band_solve_nopiv_ku<2>(ku, y, work, ab, n, n_lines, s_line, 1, 1, st, scale, add, out); break;
+        case 3: rc = band_solve_nopiv_ku<3>(ku, y, work, ab, n, n_lines, s_line, 1, 1, st, scale, add, out); break;
+        case 4: rc = band_solve_nopiv_ku<4>(ku, y, work, ab, n, n_lines, s_line, 1, 1, st, scale, add, out); break;
+        case 5: rc = band_solve_nopiv_ku<5>(ku, y, work, ab, n, n_lines, s_line, 1, 1, st, scale, add, out); break;
+        default: return bad_arg(5, "kl must be 0..5");
+    }
+    if (rc) return rc;
+    CHECK_LAUNCH("poms_band_solve_axis_fused");
     return 0;
 }
 

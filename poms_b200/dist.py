@@ -324,7 +324,7 @@ def _spike_for(lu, V):
     return ent
 
 
-def kron_solve_bnd_slab(factors, Y, X=None):
+def kron_solve_bnd_slab(factors, Y, X=None, only_axis1=False):
     """X = (A_1 (x) .. (x) A_d)^-1 Y on a slab-partitioned space: SPIKE along axis 1, plain local
     line solves along the other axes (kron_product.kron_solve_bnd is the one-GPU version)."""
     from .kron_product import _solve_axis, BandLU
@@ -335,7 +335,7 @@ def kron_solve_bnd_slab(factors, Y, X=None):
     if X is None:
         X = StencilVector(V)
     lus = list(factors)
-    for f in lus:
+    for f in (lus[:1] if only_axis1 else lus):
         if not isinstance(f, BandLU):
             raise NotImplementedError("slab-partitioned solve takes BandLU factors")
     sp = _spike_for(lus[0], V)
@@ -372,6 +372,8 @@ def kron_solve_bnd_slab(factors, Y, X=None):
                         cop, m = sp["corrV"]
                         cop.apply(znext, X.flat[n1 - m:], (q,) + shape[1:], ld, ld, 0,
                                   accumulate=True)
+    if only_axis1:
+        return X
     src = X
     for ax in range(1, len(lus)):
         with profiling.region("band_solve_axis%d" % (ax + 1), 16 * V.local_size):

@@ -105,6 +105,41 @@ def _solve_axis(lu, src, dst, axis):
         s_outer, s_axis, n_inner, _stream()), "poms_band_solve_axis")
 
 
+def _solve_last_axis_fused(lu, src, work, out, scale, add):
+    """Last (contiguous) axis solve with out = [add +] scale * solution."""
+    V = src.space
+    shape = tuple(V.local_shape)
+    n = shape[-1]
+    assert n == lu.n and lu.nopiv
+    _lib.check(_lib.lib().poms_band_solve_axis_fused(
+        src.ptr, work.ptr, lu.ab.data_ptr(), n, lu.kl, lu.ku, int(np.prod(shape[:-1])), V.ld,
+        float(scale), add.ptr if add is not None else None, out.ptr, _stream()),
+        "poms_band_solve_axis_fused")
+
+
+def kron_solve_bnd_update(factors, Y, work, out, scale, add=None):
+    """out = [add +] scale * (A_1 (x) .. (x) A_d)^-1 Y with the scaling / accumulation fused into
+    the last line solve (EXTENSION: smoother update of mg.Hierarchy.smooth).  `work` receives
+    intermediates; factors must be no-pivot BandLU objects."""
+    V = Y.space
+    lus = list(factors)
+    if V.slab is not None and V.slab.size > 1:
+        from .dist import kron_solve_bnd_slab
+        kron_solve_bnd_slab(lus[:1] + [None] * (len(lus) - 1), Y, work, only_axis1=True)
+        src = work
+        first = 1
+    else:
+        src = Y
+        first = 0
+    for ax in range(first, len(lus) - 1):
+        with profiling.region("band_solve_axis%d" % (ax + 1), 16 * V.local_size):
+            _solve_axis(lus[ax], src, work, ax)
+        src = work
+    with profiling.region("band_solve_axis%d" % len(lus), (16 if add is None else 24) * V.local_size):
+        _solve_last_axis_fused(lus[-1], src, work, out, scale, add)
+    return out
+
+
 def kron_solve_bnd(factors, Y, X=None):
     """X = (A_1 (x) .. (x) A_d)^-1 Y with pre-factored banded A_a (BandLU or the reference's
     [A_bnd, la, ua, piv] lists); dgbtrs sweeps along axis 1, then 2 (, then 3) as in

@@ -28,7 +28,7 @@ from . import profiling
 from .multilevels import knots_to_insert
 from .stencil import (StencilVectorSpace, StencilVector, KronSumMatrix, DeviceContext,
                       _stream, EPI_STORE, EPI_RESID, EPI_DINV)
-from .kron_product import BandLU, kron_solve_bnd
+from .kron_product import BandLU, kron_solve_bnd, kron_solve_bnd_update
 from . import solvers
 
 __all__ = ["Transfer", "DistTransfer", "CoarseSolver", "two_grid", "Hierarchy", "vcycle", "mg_pcg",
@@ -452,6 +452,17 @@ class Hierarchy:
         delta = 0.5 * (lv.lmax - lv.lmin)
         sigma = theta / delta
         rho = 1.0 / sigma
+        if self.smoother == "glt" and self.nu == 1 and all(lu.nopiv for lu in lv.glt_lu):
+            # one step: x <- x + (1/theta) B^-1 (b - A x); the update is fused into the last line
+            # solve (d = c1*d + c2*z with c1 = 0, so x + d == x + c2*z)
+            work = StencilVector(V, zero=False)
+            if zero_guess:
+                kron_solve_bnd_update(lv.glt_lu, b, work, x, 1.0 / theta)
+            else:
+                r = StencilVector(V, zero=False)
+                A.apply(x, r, EPI_RESID, b=b)
+                kron_solve_bnd_update(lv.glt_lu, r, work, x, 1.0 / theta, add=x)
+            return x
         r = StencilVector(V, zero=False)
         z = StencilVector(V, zero=False) if self.smoother == "glt" else r
         d = StencilVector(V, zero=False)      # written (c1 = 0) by the first Chebyshev step
