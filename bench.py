@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--smoother", default="glt", choices=["glt", "jacobi"])
     ap.add_argument("--nu", type=int, default=1)
+    ap.add_argument("--rhs", default="auto", choices=["auto", "ones", "manufactured"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     args = ap.parse_args()
@@ -188,7 +189,25 @@ def main():
     V = h.levels[0].V
     dof_global = int(np.prod(V.npts))
     b = StencilVector(V)
-    b.data.fill_(1.0)
+    rhs = args.rhs
+    if rhs == "auto":
+        # b = 1 (mg_jac.py:59-61) is a coefficient vector, not a load vector: in 2-D at 2048^2 and
+        # beyond |A||x| / |b| ~ 4e6, so the TRUE relative residual floors at ~5e-10 in fp64 whatever
+        # the solver does.  The 2-D configs therefore use the reference's other right-hand side,
+        # b = A x0 with x0[i] = i1 + i2 + 1 (sources/tests/test_pcg.py:52-58).
+        rhs = "ones" if ndim == 3 else "manufactured"
+    if rhs == "ones":
+        b.data.fill_(1.0)
+    else:
+        x0 = StencilVector(V)
+        idx = [torch.arange(V.starts[a] if a == 0 else 0,
+                            (V.ends[a] + 1) if a == 0 else V.npts[a], dtype=torch.float64,
+                            device=dev) for a in range(ndim)]
+        ramp = idx[0].reshape([-1] + [1] * (ndim - 1)) + 1.0
+        for a in range(1, ndim):
+            ramp = ramp + idx[a].reshape([1] * a + [-1] + [1] * (ndim - 1 - a))
+        x0.data.copy_(ramp)
+        b = h.levels[0].A.dot(x0)
     L = _lib.lib()
 
     def barrier():
@@ -232,7 +251,7 @@ def main():
 
     # ---- e2e: host buffers, H2D + solve + D2H inside the timed region -------------------------
     nloc = V.local_size
-    b_host = torch.ones(V.local_shape, dtype=torch.float64).pin_memory()
+    b_host = b.data.cpu().pin_memory()
     x_host = torch.empty(V.local_shape, dtype=torch.float64).pin_memory()
 
     def solve_host():
@@ -286,7 +305,10 @@ def main():
                    "ndim": ndim, "p": p, "elements": Ns, "dof": dof_global, "domain": lengths,
                    "solver": "pcg + V(%d,%d) %s-Chebyshev multigrid, tol 1e-10 relative"
                              % (args.nu, args.nu, args.smoother),
-                   "iterations": info["niter"], "levels": len(h.levels),
+                   "rhs": "b = 1 (mg_jac.py:59-61)" if rhs == "ones" else
+                          "b = A x0, x0[i] = sum(i_a) + 1 (tests/test_pcg.py:52-58)",
+                   "iterations": info["niter"], "restarts": info.get("restarts", 0),
+                   "levels": len(h.levels),
                    "rel_residual_reported": info["res_norm"] / info["res_norm0"],
                    "rel_residual_true": true_rel,
                    "l2_note": "vectors are %.0f MB each, larger than the 126 MB L2"

@@ -146,6 +146,19 @@ int poms_band_solve_axis(const double* y, double* x, const double* ab, const int
                          int64_t n_inner, void* stream);
 
 /*
+ * No-pivot banded solve for FEW lines (2-D grids: only n lines of length n exist, far too few
+ * for 148 SMs): every line is cut into chunks of `chunk` entries that start `warm_*` entries early
+ * from a zero state.  Valid when the homogeneous solutions of the two triangular recurrences decay
+ * below rounding within the warm-up (diagonally dominant SPD bands: mass, GLT); the caller checks
+ * that on the host for the given factor.  y -> work (forward), work -> x (backward); work must not
+ * alias y or x.
+ */
+int poms_band_solve_axis_chunked(const double* y, double* x, double* work, const double* ab, int n,
+                                 int kl, int ku, int64_t n_outer, int64_t s_outer, int64_t s_axis,
+                                 int64_t n_inner, int chunk, int warm_fwd, int warm_bwd,
+                                 void* stream);
+
+/*
  * No-pivot banded solve along the CONTIGUOUS axis with a fused epilogue:
  *   out = [add +] scale * T^-1 y      (work receives the forward-substitution intermediate)
  * EXTENSION used by the multi-level smoother: the Chebyshev / Richardson update

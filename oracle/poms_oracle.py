@@ -528,12 +528,17 @@ def two_grid(A, P1s, Ac_dense, b, post="jac", M1=None, M2=None, p=None, log_pre=
 # =============================================================================================
 
 
-def pcg_relative(A, psolve, b, x0=None, tol=1e-10, maxiter=200, log=None):
+def pcg_relative(A, psolve, b, x0=None, tol=1e-10, maxiter=200, log=None, abs_thresh=None):
     """pcg with the BASELINE metric's rule ||r|| <= tol*||r0|| instead of the reference's."""
     x = 0.0 * b.copy() if x0 is None else x0.copy()
     r = b - A.dot(x)
     nrmr0 = sqrt(_dot(r, r, log))
     thresh = (tol * nrmr0) ** 2
+    if abs_thresh is not None:
+        thresh = abs_thresh
+        if nrmr0 * nrmr0 <= thresh:
+            return x, {"niter": 0, "success": True, "res_norm": nrmr0, "history": np.zeros(0),
+                       "res_norm0": nrmr0}
     s = psolve(A, r)
     p = s
     sr = _dot(s, r, log)
@@ -634,6 +639,24 @@ class MGHierarchy:
         x = x + prolong(lv["P1s"], self.vcycle(l + 1, restrict(lv["P1s"], r)))
         return self.smooth(lv, b, x, False)
 
-    def mg_pcg(self, b, tol=1e-10, maxiter=200, log=None):
-        return pcg_relative(self.levels[0]["A"], lambda A_, r: self.vcycle(0, r), b, tol=tol,
-                            maxiter=maxiter, log=log)
+    def mg_pcg(self, b, tol=1e-10, maxiter=200, log=None, max_restarts=3):
+        A = self.levels[0]["A"]
+
+        def psolve(A_, r):
+            return self.vcycle(0, r)
+
+        x, info = pcg_relative(A, psolve, b, tol=tol, maxiter=maxiter, log=log)
+        target = (tol * info["res_norm0"]) ** 2
+        info["restarts"] = 0
+        while info["restarts"] < max_restarts and info["niter"] < maxiter:
+            x2, i2 = pcg_relative(A, psolve, b, x0=x, tol=tol, maxiter=maxiter - info["niter"],
+                                  log=log, abs_thresh=target)
+            info["res_norm"] = i2["res_norm"] if i2["niter"] else i2["res_norm0"]
+            if i2["niter"] == 0:
+                break
+            x = x2
+            info["niter"] += i2["niter"]
+            info["history"] = np.concatenate([info["history"], i2["history"]])
+            info["restarts"] += 1
+        info["success"] = bool(info["res_norm"] ** 2 <= target)
+        return x, info

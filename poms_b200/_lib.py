@@ -36,6 +36,8 @@ _PROTOS = {
     "poms_cheb_update": (C.c_int, [_vp, _vp, _vp, _d, _d, _l, _vp]),
     "poms_diag_scale": (C.c_int, [_vp, _vp, _vp, _l, _d, _vp, _vp, _vp]),
     "poms_band_solve_axis": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _l, _l, _l, _l, _vp]),
+    "poms_band_solve_axis_chunked": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _l, _l, _l, _l,
+                                              _i, _i, _i, _vp]),
     "poms_band_solve_axis_fused": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _l, _l, _d, _vp, _vp, _vp]),
     "poms_axis_gather": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _l, _l, _l, _l, _l, _l,
                                   _i, _vp]),

@@ -1304,6 +1304,112 @@ static int band_solve_nopiv_ku(int ku, const double* y, double* x, const double*
     return 0;
 }
 
+// (c) few lines (2-D grids): CHUNKED substitution.  For the diagonally dominant SPD bands of this
+//     code the homogeneous solutions of both triangular recurrences decay geometrically, so a line
+//     can be cut into chunks that each start `warm` entries early from a zero state: after the
+//     warm-up the state agrees with the sequential sweep to rounding (the caller verifies the decay
+//     for the given factor before choosing this path).  One thread per (line, chunk); the forward
+//     and backward sweeps are separate launches (y -> work, work -> x).
+template <int KL, int KU, bool FWD>
+__global__ void __launch_bounds__(128) band_chunk_kernel(
+    const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ ab, int n,
+    int64_t n_outer, int64_t s_outer, int64_t s_axis, int64_t n_inner, int chunk, int warm,
+    int nchunks) {
+    constexpr int KD = KL + KU;
+    const int64_t nlines = n_outer * n_inner;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nlines * nchunks) return;
+    const int ck = (int)(t / nlines);
+    const int64_t line = t - (int64_t)ck * nlines;
+    const int64_t o = line / n_inner, c = line - o * n_inner;
+    const double* il = in + o * s_outer + c;
+    double* ol = out + o * s_outer + c;
+    const int jb = ck * chunk, je = min(n, jb + chunk);
+    if (FWD) {
+        double z[KL > 0 ? KL : 1];
+#pragma unroll
+        for (int m = 0; m < KL; ++m) z[m] = 0.0;
+        const int j0 = max(0, jb - warm);
+        for (int j = j0; j < je; ++j) {
+            double s = il[(int64_t)j * s_axis];
+#pragma unroll
+            for (int m = KL; m >= 1; --m)
+                if (j - m >= j0) s = fma(-__ldg(ab + (int64_t)(KD + m) * n + (j - m)), z[m - 1], s);
+            if (j >= jb) ol[(int64_t)j * s_axis] = s;
+#pragma unroll
+            for (int m = KL - 1; m >= 1; --m) z[m] = z[m - 1];
+            if (KL > 0) z[0] = s;
+        }
+    } else {
+        double w[KU > 0 ? KU : 1];
+#pragma unroll
+        for (int m = 0; m < KU; ++m) w[m] = 0.0;
+        const int jt = min(n, je + warm);
+        for (int j = jt - 1; j >= jb; --j) {
+            double s = il[(int64_t)j * s_axis];
+#pragma unroll
+            for (int m = KU; m >= 1; --m)
+                if (j + m < jt) s = fma(-__ldg(ab + (int64_t)(KD - m) * n + (j + m)), w[m - 1], s);
+            s *= 1.0 / __ldg(ab + (int64_t)KD * n + j);
+            if (j < je) ol[(int64_t)j * s_axis] = s;
+#pragma unroll
+            for (int m = KU - 1; m >= 1; --m) w[m] = w[m - 1];
+            if (KU > 0) w[0] = s;
+        }
+    }
+}
+
+template <int KL>
+static int band_chunk_ku(int ku, const double* y, double* x, double* work, const double* ab, int n,
+                         int64_t n_outer, int64_t s_outer, int64_t s_axis, int64_t n_inner,
+                         int chunk, int warm_f, int warm_b, cudaStream_t st) {
+    const int nchunks = (n + chunk - 1) / chunk;
+    const int64_t threads = n_outer * n_inner * nchunks;
+    const int grid = (int)((threads + 127) / 128);
+#define BC(KU_)                                                                                   \
+    band_chunk_kernel<KL, KU_, true><<<grid, 128, 0, st>>>(y, work, ab, n, n_outer, s_outer,      \
+                                                           s_axis, n_inner, chunk, warm_f, nchunks); \
+    band_chunk_kernel<KL, KU_, false><<<grid, 128, 0, st>>>(work, x, ab, n, n_outer, s_outer,     \
+                                                            s_axis, n_inner, chunk, warm_b, nchunks);
+    switch (ku) {
+        case 0: BC(0); break;
+        case 1: BC(1); break;
+        case 2: BC(2); break;
+        case 3: BC(3); break;
+        case 4: BC(4); break;
+        case 5: BC(5); break;
+        default: return bad_arg(7, "ku must be 0..5");
+    }
+#undef BC
+    return 0;
+}
+
+extern "C" int poms_band_solve_axis_chunked(const double* y, double* x, double* work,
+                                            const double* ab, int n, int kl, int ku,
+                                            int64_t n_outer, int64_t s_outer, int64_t s_axis,
+                                            int64_t n_inner, int chunk, int warm_fwd, int warm_bwd,
+                                            void* stream) {
+    if (!y || !x || !work || !ab) return bad_arg(1, "null pointer");
+    if (work == y || work == x) return bad_arg(3, "work must not alias y or x");
+    if (n < 1 || n_outer < 1 || n_inner < 1) return bad_arg(5, "extent");
+    if (chunk < 8 || warm_fwd < 0 || warm_bwd < 0) return bad_arg(12, "chunk/warm");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    switch (kl) {
+        case 0: rc = band_chunk_ku<0>(ku, y, x, work, ab, n, n_outer, s_outer, s_axis, n_inner, chunk, warm_fwd, warm_bwd, st); break;
+        case 1: rc = band_chunk_ku<1>(ku, y, x, work, ab, n, n_outer, s_outer, s_axis, n_inner, chunk, warm_fwd, warm_bwd, st); break;
+        case 2: rc = band_chunk_ku<2>(ku, y, x, work, ab, n, n_outer, s_outer, s_axis, n_inner, chunk, warm_fwd, warm_bwd, st); break;
+        case 3: rc = band_chunk_ku<3>(ku, y, x, work, ab, n, n_outer, s_outer, s_axis, n_inner, chunk, warm_fwd, warm_bwd, st); break;
+        case 4: rc = band_chunk_ku<4>(ku, y, x, work, ab, n, n_outer, s_outer, s_axis, n_inner, chunk, warm_fwd, warm_bwd, st); break;
+        case 5: rc = band_chunk_ku<5>(ku, y, x, work, ab, n, n_outer, s_outer, s_axis, n_inner, chunk, warm_fwd, warm_bwd, st); break;
+        default: return bad_arg(6, "kl must be 0..5");
+    }
+    if (rc) return rc;
+    g_launches++;   // two launches
+    CHECK_LAUNCH("poms_band_solve_axis_chunked");
+    return 0;
+}
+
 extern "C" int poms_band_solve_axis_fused(const double* y, double* work, const double* ab, int n,
                                           int kl, int ku, int64_t n_lines, int64_t s_line,
                                           double scale, const double* add, double* out,

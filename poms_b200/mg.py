@@ -327,22 +327,44 @@ def two_grid(A, transfer, coarse, b, Vc, post="jac", M1=None, M2=None, p=None,
 # EXTENSION: multi-level V-cycle and MG-preconditioned CG
 # ==========================================================================================
 def _gen_eig_max(Kb, Tb):
-    """Largest generalised eigenvalue of K x = mu T x for banded SPD 1-D matrices (host)."""
+    """Largest generalised eigenvalue of K x = mu T x for banded SPD 1-D matrices (host).
+    n <= 1500: dense LAPACK (exact; what the oracle does).  Larger n: Lanczos on T^-1 K with banded
+    solves, tolerance 1e-3 (the top of these spectra is a dense cluster: a tight tolerance took
+    256 s at n = 8197, and the Chebyshev interval carries a 10 % safety factor anyway)."""
     n = Kb.shape[0]
     if n <= 1500:
         from scipy.linalg import eigh
         return float(eigh(bs.band_to_dense(Kb), bs.band_to_dense(Tb), eigvals_only=True,
                           subset_by_index=[n - 1, n - 1])[0])
-    from scipy.sparse import csr_matrix
-    from scipy.sparse.linalg import eigsh
+    from scipy.linalg import solve_banded
+    from scipy.sparse.linalg import eigsh, LinearOperator
 
-    def sp(band):
+    def trimmed(band):
         p = (band.shape[1] - 1) // 2
-        from scipy.sparse import diags
-        return diags([band[max(0, -k):n - max(0, k), k + p] for k in range(-p, p + 1)],
-                     list(range(-p, p + 1)), format="csc")
-    return float(eigsh(sp(Kb), k=1, M=sp(Tb), which="LA", return_eigenvectors=False,
-                       tol=1e-8)[0])
+        q = p
+        while q > 0 and not band[:, p - q].any() and not band[:, p + q].any():
+            q -= 1
+        return band[:, p - q:p + q + 1], q
+
+    def apply(band, q, x):
+        y = np.zeros(n)
+        for k in range(-q, q + 1):
+            lo, hi = max(0, -k), min(n, n - k)
+            y[lo:hi] += band[lo:hi, k + q] * x[lo + k:hi + k]
+        return y
+
+    Kt, qk = trimmed(Kb)
+    Tt, qt = trimmed(Tb)
+    ab = np.zeros((2 * qt + 1, n))
+    for k in range(-qt, qt + 1):
+        i = np.arange(max(0, -k), min(n, n - k))
+        ab[qt - k, i + k] = Tt[i, k + qt]
+    op = LinearOperator((n, n), matvec=lambda v: apply(Kt, qk, v), dtype=float)
+    M = LinearOperator((n, n), matvec=lambda v: apply(Tt, qt, v), dtype=float)
+    Minv = LinearOperator((n, n), matvec=lambda v: solve_banded((qt, qt), ab, v), dtype=float)
+    v0 = np.cos(np.arange(n) * 0.7) + 1.5          # deterministic start vector
+    return float(eigsh(op, k=1, M=M, Minv=Minv, which="LA", tol=1e-3, ncv=24, v0=v0,
+                       return_eigenvectors=False)[0])
 
 
 class Level:
@@ -509,7 +531,8 @@ def vcycle(h, l, b):
     return x
 
 
-def mg_pcg(h, b, x0=None, tol=1e-10, maxiter=200, criterion="relative", verbose=False):
+def mg_pcg(h, b, x0=None, tol=1e-10, maxiter=200, criterion="relative", verbose=False,
+           max_restarts=3):
     """MG-preconditioned CG: the reference's `pcg` driver (same operation order) with one V-cycle
     as `psolve`.  criterion='relative': stop when ||r|| <= tol*||r0|| (the BASELINE metric);
     criterion='reference': the reference's own mixed rule r.r < tol*||r0||."""
@@ -520,5 +543,23 @@ def mg_pcg(h, b, x0=None, tol=1e-10, maxiter=200, criterion="relative", verbose=
 
     if criterion == "reference":
         return solvers.pcg(A, psolve, b, x0=x0, tol=tol, maxiter=maxiter, verbose=verbose)
-    return solvers._pcg_driver(A, psolve, b, x0, tol, maxiter, verbose, "MG-PCG solver:",
-                               relative=True)
+    x, info = solvers._pcg_driver(A, psolve, b, x0, tol, maxiter, verbose, "MG-PCG solver:",
+                                  relative=True)
+    # The CG recurrence residual drifts from b - A x on ill-conditioned problems (2-D 2048^2: 1e-10
+    # claimed, 9e-10 true).  Verify with the TRUE residual and restart from x until it meets the
+    # target (each restart recomputes r = b - A x; it returns at once when the target is met).
+    target = (tol * info["res_norm0"]) ** 2
+    info["restarts"] = 0
+    while info["restarts"] < max_restarts and info["niter"] < maxiter:
+        x2, i2 = solvers._pcg_driver(A, psolve, b, x, tol, maxiter - info["niter"], verbose,
+                                     "MG-PCG restart:", relative=True, abs_thresh=target)
+        info["res_norm"] = i2["res_norm"] if i2["niter"] else i2["res_norm0"]
+        info["true_res_norm"] = i2["res_norm0"] if not i2["niter"] else None
+        if i2["niter"] == 0:
+            break
+        x = x2
+        info["niter"] += i2["niter"]
+        info["history"] = list(info["history"]) + list(i2["history"])
+        info["restarts"] += 1
+    info["success"] = bool(info["res_norm"] ** 2 <= target)
+    return x, info

@@ -61,7 +61,7 @@ def _residual(A, b, x0, ctx):
     return x, r
 
 
-def _pcg_driver(A, psolve, b, x0, tol, maxiter, verbose, title, relative=False):
+def _pcg_driver(A, psolve, b, x0, tol, maxiter, verbose, title, relative=False, abs_thresh=None):
     _check_shapes(A, b, x0)
     V = b.space
     ctx = DeviceContext.get(V.device)
@@ -71,6 +71,11 @@ def _pcg_driver(A, psolve, b, x0, tol, maxiter, verbose, title, relative=False):
     # reference rule (lines 111-113): r.r < tol*||r0|| (squared vs unsquared norm);
     # relative=True (EXTENSION, the BASELINE metric): ||r|| <= tol*||r0||
     thresh = (tol * nrmr0) ** 2 if relative else tol * nrmr0
+    if abs_thresh is not None:      # restart of mg_pcg: absolute target on r.r (EXTENSION)
+        thresh = abs_thresh
+        if nrmr0 * nrmr0 <= thresh:
+            return x, {"niter": 0, "success": True, "res_norm": nrmr0, "history": [],
+                       "res_norm0": nrmr0}
     s = psolve(A, r)
     p = s  # the reference aliases p = s too (line 90); s is rebound, never mutated
     cur = S_SR0
