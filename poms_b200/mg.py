@@ -379,7 +379,7 @@ class Hierarchy:
     """
 
     def __init__(self, p, N, ndim=None, Nc=8, device="cuda", smoother="glt", nu=1, ratio=4.0,
-                 safety=1.1, slab=None, lengths=None):
+                 safety=1.1, slab=None, lengths=None, min_planes=32):
         if np.isscalar(N):
             N = [int(N)] * int(ndim)
         # domain [0, L_1] x .. x [0, L_d] (default the unit cube).  Weak scaling extends the domain
@@ -395,12 +395,13 @@ class Hierarchy:
             lv.N = list(Ns)
             lv.knots = [bs.make_open_knots(p, n + p) * L for n, L in zip(Ns, self.lengths)]
             lv.A = KronSumMatrix.poisson(p, lv.knots)
-            # a level stays slab-partitioned while every slab keeps enough planes for the p-wide
-            # halo and the 2q interface planes of the partitioned solve; below that it is gathered
-            # and every rank works on the whole (small) grid redundantly
+            # a level stays slab-partitioned while every slab keeps at least `min_planes` planes
+            # (and enough for the p-wide halo and the 2q interface planes of the partitioned solve);
+            # below that the per-operation latency of the exchanges exceeds the work, so the level is
+            # gathered and every rank works on the whole (small) grid redundantly
             lv.distributed = (slab is not None and slab.size > 1
                               and (not self.levels or self.levels[-1].distributed)
-                              and (Ns[0] + p) >= slab.size * max(2 * p + 2, 8))
+                              and (Ns[0] + p) >= slab.size * max(2 * p + 2, min_planes))
             lv.V = StencilVectorSpace([n + p for n in Ns], [p] * self.ndim,
                                       [False] * self.ndim, device=self.device,
                                       slab=slab if lv.distributed else None)

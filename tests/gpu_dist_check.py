@@ -60,7 +60,7 @@ for (p, N) in ((3, (32 * world, 16, 24)), (2, (64, 40)), (3, (64 * world, 32))):
     # MG-PCG: identical iteration count and history vs the oracle
     # isotropic weak-scaling geometry: the domain is as many units long as the grid is wide
     lengths = [n / min(N) for n in N]
-    h = Hierarchy(p, list(N), device=dev, slab=slab, lengths=lengths)
+    h = Hierarchy(p, list(N), device=dev, slab=slab, lengths=lengths, min_planes=8)
     ho = po.MGHierarchy(p, list(N), lengths=lengths)
     bb = StencilVector(h.levels[0].V)
     bb.data.fill_(1.0)
