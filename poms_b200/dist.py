@@ -305,6 +305,24 @@ def _spike_for(lu, V):
     q, G, r = st.q, st.G, slab.rank
     dev = V.device
     ent = {"setup": st, "q": q, "local_lu": BandLU.from_band(st.local_bands[r], dev)}
+    nl_all = [e - s_ + 1 for s_, e in table]
+    # Thick slabs: the spikes have decayed below rounding before they reach the far side of a slab
+    # (W^bot = V^top = 0 to 1e-17), so the reduced system splits into one independent 2q x 2q
+    # system per interface that only involves the two slabs touching it: a q-plane neighbour
+    # exchange replaces the all-gather of every interface plane.
+    local = all(st.mW[k] <= nl_all[k] - q and st.mV[k] <= nl_all[k] - q for k in range(G))
+    ent["local"] = local
+    if local:
+        def iface_inverse(lo):   # interface between slabs lo and lo+1: unknowns [bot_lo ; top_lo+1]
+            nlo = nl_all[lo]
+            S2 = np.eye(2 * q)
+            S2[:q, q:] = st.V[lo][nlo - q:]          # bot_lo + V^bot_lo top_{lo+1}
+            S2[q:, :q] = st.W[lo + 1][:q]            # top_{lo+1} + W^top_{lo+1} bot_lo
+            return np.linalg.inv(S2)
+        if r > 0:       # need bot_{r-1}: first q rows of the inverse of interface (r-1, r)
+            ent["red_lo"] = _AxisOp(np.zeros(q, dtype=np.int32), iface_inverse(r - 1)[:q], 2 * q, dev)
+        if r < G - 1:   # need top_{r+1}: last q rows of the inverse of interface (r, r+1)
+            ent["red_hi"] = _AxisOp(np.zeros(q, dtype=np.int32), iface_inverse(r)[q:], 2 * q, dev)
     # rows of Sinv this rank needs: bot_{r-1} and top_{r+1}
     rows = []
     if r > 0:
@@ -346,7 +364,31 @@ def kron_solve_bnd_slab(factors, Y, X=None, only_axis1=False):
     # 1. local diagonal-block solves along axis 1
     with profiling.region("band_solve_axis1", 16 * V.local_size):
         _solve_axis(sp["local_lu"], Y, X, 0)
-    if slab.size > 1:
+    if slab.size > 1 and sp["local"]:
+        with profiling.region("spike_interface", 0, launches=4):
+            r, G = slab.rank, slab.size
+            glo = q if r > 0 else 0
+            ghi = q if r < G - 1 else 0
+            tail = tuple(X.flat.shape[1:])
+            # 2. [from below | my top | my bottom | from above]: one q-plane neighbour exchange
+            buf = torch.empty((glo + 2 * q + ghi,) + tail, dtype=X.flat.dtype, device=X.flat.device)
+            buf[glo:glo + q] = X.flat[:q]
+            buf[glo + q:glo + 2 * q] = X.flat[n1 - q:]
+            slab.exchange_planes(buf, 2 * q, glo, ghi, q)
+            # 3./4. per-interface 2q x 2q solves and the truncated spike corrections
+            if r > 0:
+                zprev = torch.empty((q,) + tail, dtype=buf.dtype, device=buf.device)
+                sp["red_lo"].apply(buf[0:2 * q], zprev, (2 * q,) + shape[1:], ld, ld, 0)
+                if "corrW" in sp:
+                    cop, m = sp["corrW"]
+                    cop.apply(zprev, X.flat[:m], (q,) + shape[1:], ld, ld, 0, accumulate=True)
+            if r < G - 1:
+                znext = torch.empty((q,) + tail, dtype=buf.dtype, device=buf.device)
+                sp["red_hi"].apply(buf[glo + q:glo + 3 * q], znext, (2 * q,) + shape[1:], ld, ld, 0)
+                if "corrV" in sp:
+                    cop, m = sp["corrV"]
+                    cop.apply(znext, X.flat[n1 - m:], (q,) + shape[1:], ld, ld, 0, accumulate=True)
+    elif slab.size > 1:
         with profiling.region("spike_interface", 0, launches=3):
             # 2. interface planes of every slab -> everyone
             zl = torch.cat([X.flat[:q], X.flat[n1 - q:]], dim=0).contiguous()

@@ -32,7 +32,7 @@ def check(name, cond, info=""):
     ok = ok and bool(flag.item())
 
 
-for (p, N) in ((3, (32 * world, 16, 24)), (2, (64, 40)), (3, (64 * world, 32))):
+for (p, N) in ((3, (32 * world, 16, 24)), (2, (64, 40)), (3, (64 * world, 32)), (3, (128 * world, 16, 16))):
     d = len(N)
     knots = [bs.make_open_knots(p, n + p) for n in N]
     npts = [n + p for n in N]
