@@ -313,8 +313,15 @@ def main():
         k = kern[dominant]
         avg_ms = k["ms"] / k["launches"]
         achieved = k["bytes"] / k["launches"] / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f).get(dominant)
+            if tj:
+                traffic = tj["traffic_over_algorithmic"] * k["bytes"] / k["launches"]
         roof = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "launches": k["launches"],
                 "avg_launch_ms": avg_ms, "share_of_step": k["share"],
                 "algorithmic_bytes_per_launch": k["bytes"] / k["launches"]}
