@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="c5", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--smoother", default="glt", choices=["glt", "jacobi"])
+    ap.add_argument("--smoother", default="auto", choices=["auto", "glt", "glt_poly", "jacobi"])
     ap.add_argument("--nu", type=int, default=1)
     ap.add_argument("--rhs", default="auto", choices=["auto", "ones", "manufactured"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -199,6 +199,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         slab = Slab(dist.group.WORLD, dev)
     ndim, p, N, desc = CONFIGS[args.config]
+    if args.smoother == "auto":
+        # polynomial GLT smoother (three fused Kronecker band passes) where its second factor fits
+        # the kernels' half-bandwidth limit (p <= 3); exact GLT line solves otherwise
+        args.smoother = "glt_poly" if 2 <= p <= 3 else "glt"
     Ns = [N] * ndim
     if world > 1:
         Ns[0] = N * world          # weak scaling: N element planes per GPU along axis 1

@@ -42,6 +42,7 @@ int64_t poms_launch_count(void);
 #define POMS_EPI_RESID  1  /* y = b - v                  ; dot += y*y   (r.r)                */
 #define POMS_EPI_JACOBI 2  /* y = x + om*(b - v)/diag(A) ; dot += dr*dr (damped Jacobi sweep) */
 #define POMS_EPI_DINV   3  /* y = om*(b - v)/diag(A)     ; dot += y*y   (Jacobi-preconditioned residual) */
+#define POMS_EPI_AXPY   4  /* y = b + om*v               ; dot += (om*v)^2 (EXTENSION: smoother update) */
 
 /*
  * Kronecker-structured banded mat-vec, one fused pass (16 B/DOF algorithmic).

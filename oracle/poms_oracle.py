@@ -563,6 +563,28 @@ def pcg_relative(A, psolve, b, x0=None, tol=1e-10, maxiter=200, log=None, abs_th
                "history": np.sqrt(np.array(hist)), "res_norm0": nrmr0}
 
 
+def _symbol_range(band):
+    n, w = band.shape
+    p = (w - 1) // 2
+    row = band[n // 2]
+    th = np.linspace(0.0, np.pi, 4097)
+    m = row[p] + 2.0 * sum(row[p + k] * np.cos(k * th) for k in range(1, p + 1))
+    return float(m.min()), float(m.max())
+
+
+def _cheb_inverse_poly(lmin, lmax, degree):
+    """q(t) = (1 - T_{k+1}((a-t)/d)/T_{k+1}(a/d))/t in monomial coefficients c_0..c_k."""
+    from numpy.polynomial import chebyshev as C, polynomial as P
+    a, d = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
+    mono = C.Chebyshev.basis(degree + 1).convert(kind=np.polynomial.Polynomial).coef
+    out, powr = np.zeros(1), np.ones(1)
+    for c in mono:
+        out = P.polyadd(out, c * powr)
+        powr = P.polymul(powr, np.array([a / d, -1.0 / d]))
+    out = out / C.Chebyshev.basis(degree + 1)(a / d)
+    return P.polysub(np.ones(1), out)[1:]
+
+
 class MGHierarchy:
     def __init__(self, p, N, Nc=8, smoother="glt", nu=1, ratio=4.0, safety=1.1, lengths=None):
         from scipy.linalg import eigh
@@ -606,6 +628,24 @@ class MGHierarchy:
                     muK = eigh(KM, band_to_dense(bands[a]), eigvals_only=True)[-1]
                     best = max(best, muK * float(np.prod([muM[c] for c in range(d) if c != a])))
                 lv["lmax"] = safety * best
+            elif smoother == "glt_poly":
+                # restates poms_b200/mg.py 'glt_poly': B^-1 ~ q(T) per axis, q = degree-3 Chebyshev
+                # approximation of 1/t on the symbol range of T widened by 2 %
+                q = max(2 * p - 1, 1)
+                bands = [glt_band(p, n, degree=q) for n in A.npts]
+                lv["gband"] = bands
+                lv["qc"] = []
+                for b_ in bands:
+                    lo, hi = _symbol_range(b_)
+                    lv["qc"].append(_cheb_inverse_poly(lo * 0.98, hi * 1.02, 3))
+                muM = [eigh(band_to_dense(lv["Mb"][a]), band_to_dense(bands[a]),
+                            eigvals_only=True)[-1] for a in range(d)]
+                best = 0.0
+                for a in range(d):
+                    KM = band_to_dense(lv["Kb"][a]) + band_to_dense(lv["Mb"][a])
+                    muK = eigh(KM, band_to_dense(bands[a]), eigvals_only=True)[-1]
+                    best = max(best, muK * float(np.prod([muM[c] for c in range(d) if c != a])))
+                lv["lmax"] = safety * best      # q(t) t = 0.9 at the high-frequency end: no inflation needed
             else:
                 raise NotImplementedError
             lv["lmin"] = lv["lmax"] / ratio
@@ -613,6 +653,17 @@ class MGHierarchy:
     def smooth(self, lv, b, x, zero_guess):
         A = lv["A"]
         theta = 0.5 * (lv["lmax"] + lv["lmin"])
+        if self.smoother == "glt_poly":
+            for k in range(self.nu):
+                z = b if (k == 0 and zero_guess) else b - A.dot(x)
+                for ax in range(A.ndim):        # Horner evaluation of q(T) along every axis
+                    c = lv["qc"][ax]
+                    y = c[-1] * z
+                    for cf in c[-2::-1]:
+                        y = apply_band(lv["gband"][ax], y, ax) + cf * z
+                    z = y
+                x = x + z / theta
+            return x
         delta = 0.5 * (lv["lmax"] - lv["lmin"])
         sigma = theta / delta
         rho = 1.0 / sigma

@@ -289,3 +289,86 @@ def band_lu(band):
     if info != 0:
         raise np.linalg.LinAlgError("dgbtrf failed with info=%d" % info)
     return lub, kl, ku, piv
+
+
+# ---------------------------------------------------------------------------------------------
+# polynomial approximation of a banded SPD Toeplitz-type inverse (EXTENSION: smoother of mg.py)
+# ---------------------------------------------------------------------------------------------
+def symbol_range(band):
+    """[min, max] of the symbol t_0 + 2 sum_k t_k cos(k theta) of the middle row of a symmetric
+    band; the eigenvalues of the (truncated) Toeplitz matrix lie inside."""
+    n, w = band.shape
+    p = (w - 1) // 2
+    row = band[n // 2]
+    th = np.linspace(0.0, np.pi, 4097)
+    m = row[p] + 2.0 * sum(row[p + k] * np.cos(k * th) for k in range(1, p + 1))
+    return float(m.min()), float(m.max())
+
+
+def cheb_inverse_poly(lmin, lmax, degree):
+    """Monomial coefficients c_0..c_k of q(t) = (1 - T_{k+1}((a-t)/d) / T_{k+1}(a/d)) / t, the
+    Chebyshev approximation of 1/t on [lmin, lmax] (a, d = centre, half-width)."""
+    from numpy.polynomial import chebyshev as C, polynomial as P
+    a, d = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
+    mono = C.Chebyshev.basis(degree + 1).convert(kind=np.polynomial.Polynomial).coef
+    s_poly = np.array([a / d, -1.0 / d])
+    out, powr = np.zeros(1), np.ones(1)
+    for c in mono:
+        out = P.polyadd(out, c * powr)
+        powr = P.polymul(powr, s_poly)
+    out = out / C.Chebyshev.basis(degree + 1)(a / d)
+    num = P.polysub(np.ones(1), out)
+    return num[1:]
+
+
+def band_matmul(A, B):
+    """Band of the product of two banded matrices given as (n, 2p+1) bands."""
+    n = A.shape[0]
+    pa, pb = (A.shape[1] - 1) // 2, (B.shape[1] - 1) // 2
+    pc = pa + pb
+    Cb = np.zeros((n, 2 * pc + 1))
+    for ka in range(-pa, pa + 1):
+        for kb in range(-pb, pb + 1):
+            i = np.arange(n)
+            j = i + ka                      # A[i, j] * B[j, j + kb]
+            ok = (j >= 0) & (j < n) & (j + kb >= 0) & (j + kb < n)
+            Cb[i[ok], ka + kb + pc] += A[i[ok], ka + pa] * B[j[ok], kb + pb]
+    return Cb
+
+
+def poly_inverse_factors(band, degree=3, widen=0.02):
+    """Banded factors F_1, F_2 (half-bandwidths q and (degree-1) q) with F_2 F_1 = q_degree(T) ~ T^-1:
+    q(t) = c_k (t - r)(monic polynomial of degree k-1), r a real root (odd degree) -- two narrow band
+    passes per axis instead of one wide one.  `band` is trimmed to its true half-bandwidth q first."""
+    from numpy.polynomial import polynomial as P
+    band = np.asarray(band, dtype=np.float64)
+    p = (band.shape[1] - 1) // 2
+    q = p
+    while q > 0 and not band[:, p - q].any() and not band[:, p + q].any():
+        q -= 1
+    T = band[:, p - q:p + q + 1]
+    n = T.shape[0]
+    lo, hi = symbol_range(T)
+    c = cheb_inverse_poly(lo * (1.0 - widen), hi * (1.0 + widen), degree)
+    roots = P.polyroots(c)
+    real = roots[np.abs(roots.imag) < 1e-9 * max(1.0, np.abs(roots).max())].real
+    eye = np.zeros((n, 2 * q + 1))
+    eye[:, q] = 1.0
+    if len(real) == 0 or degree < 2:
+        F1 = c[0] * eye.copy() if degree == 0 else None
+        raise ValueError("use an odd degree >= 3 (or 2 with a real root)")
+    r = real[np.argmax(np.abs(real))]
+    rest = P.polydiv(c, np.array([-r, 1.0]))[0]          # q(t) = (t - r) * rest(t)
+    F1 = T - r * eye
+    # Horner for rest(T), starting from a diagonal band
+    F2 = np.full((n, 1), rest[-1])
+    for coef in rest[-2::-1]:
+        F2 = band_matmul(F2, T)
+        w2 = (F2.shape[1] - 1) // 2
+        F2[:, w2] += coef
+    # make the Toeplitz-interior rows bit-identical (they are equal up to rounding)
+    for F in (F1, F2):
+        w = (F.shape[1] - 1) // 2
+        if n > 4 * w + 1:
+            F[2 * w:n - 2 * w] = F[n // 2]
+    return F1, F2

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256, 2) kron_matvec3d_kernel(MV3 a) {
     }
     // diagonal pieces for the Jacobi epilogue
     double dA[E], dB[E];
-    if (EPI >= POMS_EPI_JACOBI) {
+    if (EPI == POMS_EPI_JACOBI || EPI == POMS_EPI_DINV) {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int i2 = i2_0 + ty * E + e;
@@ -315,6 +315,10 @@ __global__ void __launch_bounds__(256, 2) kron_matvec3d_kernel(MV3 a) {
                         const double rr = a.b[idx] - v;
                         a.y[idx] = rr;
                         dsum = fma(rr, rr, dsum);
+                    } else if (EPI == POMS_EPI_AXPY) {
+                        const double w_ = a.omega * v;
+                        a.y[idx] = a.b[idx] + w_;
+                        dsum = fma(w_, w_, dsum);
                     } else {
                         double dg;
                         if (FORM == POMS_FORM_SUM)
@@ -346,6 +350,7 @@ static int launch_mv3_epi(const MV3& a, int epi, dim3 grid, cudaStream_t st) {
         case POMS_EPI_RESID: kron_matvec3d_kernel<P, FORM, POMS_EPI_RESID><<<grid, 256, 0, st>>>(a); break;
         case POMS_EPI_JACOBI: kron_matvec3d_kernel<P, FORM, POMS_EPI_JACOBI><<<grid, 256, 0, st>>>(a); break;
         case POMS_EPI_DINV: kron_matvec3d_kernel<P, FORM, POMS_EPI_DINV><<<grid, 256, 0, st>>>(a); break;
+        case POMS_EPI_AXPY: kron_matvec3d_kernel<P, FORM, POMS_EPI_AXPY><<<grid, 256, 0, st>>>(a); break;
         default: return bad_arg(19, "epilogue");
     }
     return 0;
@@ -405,7 +410,7 @@ extern "C" int poms_kron_matvec_3d_ex(const double* x, double* y, const double* 
     if (n1 < 1 || n2 < 1 || n3 < 1) return bad_arg(4, "extent");
     if (ld < n3) return bad_arg(7, "ld");
     if (pld < ld * n2) return bad_arg(8, "pld");
-    if (glo < 0 || ghi < 0 || glo > p || ghi > p) return bad_arg(9, "ghost planes");
+    if (glo < 0 || ghi < 0) return bad_arg(9, "ghost planes");
     if (!m1 || !m2 || !m3) return bad_arg(13, "band pointers");
     if (form == POMS_FORM_SUM && (!k1 || !k2 || !k3)) return bad_arg(14, "k bands");
     if (dot_out && !ws) return bad_arg(22, "ws");
@@ -550,6 +555,10 @@ __global__ void __launch_bounds__(128, 4) kron_matvec2d_kernel(MV2 a) {
                             const double rr = a.b[idx] - v;
                             a.y[idx] = rr;
                             dsum = fma(rr, rr, dsum);
+                        } else if (EPI == POMS_EPI_AXPY) {
+                            const double w_ = a.omega * v;
+                            a.y[idx] = a.b[idx] + w_;
+                            dsum = fma(w_, w_, dsum);
                         } else {
                             double dg;
                             if (FORM == POMS_FORM_SUM)
@@ -583,6 +592,7 @@ static int launch_mv2_epi(const MV2& a, int epi, dim3 grid, cudaStream_t st) {
         case POMS_EPI_RESID: kron_matvec2d_kernel<P, FORM, POMS_EPI_RESID><<<grid, 128, 0, st>>>(a); break;
         case POMS_EPI_JACOBI: kron_matvec2d_kernel<P, FORM, POMS_EPI_JACOBI><<<grid, 128, 0, st>>>(a); break;
         case POMS_EPI_DINV: kron_matvec2d_kernel<P, FORM, POMS_EPI_DINV><<<grid, 128, 0, st>>>(a); break;
+        case POMS_EPI_AXPY: kron_matvec2d_kernel<P, FORM, POMS_EPI_AXPY><<<grid, 128, 0, st>>>(a); break;
         default: return bad_arg(15, "epilogue");
     }
     return 0;
@@ -604,7 +614,7 @@ extern "C" int poms_kron_matvec_2d(const double* x, double* y, const double* b, 
     if (epilogue != POMS_EPI_STORE && !b) return bad_arg(3, "b required by epilogue");
     if (n1 < 1 || n2 < 1) return bad_arg(4, "extent");
     if (ld < n2) return bad_arg(6, "ld");
-    if (glo < 0 || ghi < 0 || glo > p || ghi > p) return bad_arg(7, "ghost rows");
+    if (glo < 0 || ghi < 0) return bad_arg(7, "ghost rows");
     if (!m1 || !m2) return bad_arg(11, "band pointers");
     if (form == POMS_FORM_SUM && (!k1 || !k2)) return bad_arg(12, "k bands");
     if (dot_out && !ws) return bad_arg(18, "ws");

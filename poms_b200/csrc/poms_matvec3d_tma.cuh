@@ -68,8 +68,10 @@ struct MV3TCfg {
 #ifndef POMS_MV3_MINB
 #define POMS_MV3_MINB 2
 #endif
+// two CTAs per SM whenever registers (2p+1 partial sums per point) and shared memory allow it
+#define POMS_MV3_BLOCKS(P, FORM) (((P) <= 3 || ((P) == 4 && (FORM) == POMS_FORM_SINGLE)) ? POMS_MV3_MINB : 1)
 template <int P, int FORM, int EPI>
-__global__ void __launch_bounds__(256, (P <= 3 ? POMS_MV3_MINB : 1))
+__global__ void __launch_bounds__(256, POMS_MV3_BLOCKS(P, FORM))
 kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MV3T g) {
     using C = MV3TCfg<P>;
     constexpr int W = C::W, T3 = C::T3, TY = C::TY, E = C::E, T2 = C::T2, R2 = C::R2, C3 = C::C3,
@@ -117,7 +119,7 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         }
     }
     double dA[E], dB[E];
-    if (EPI >= POMS_EPI_JACOBI) {
+    if (EPI == POMS_EPI_JACOBI || EPI == POMS_EPI_DINV) {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int i2 = i2_0 + ty * E + e;
@@ -304,7 +306,7 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         if (emit) {
             const int64_t o = (int64_t)i1 * a.pld + poff;
             double dg1 = 0.0, dg2 = 0.0;
-            if (EPI >= POMS_EPI_JACOBI) {
+            if (EPI == POMS_EPI_JACOBI || EPI == POMS_EPI_DINV) {
                 dg1 = TWO ? __ldg(a.k1 + (int64_t)i1 * W + P) : __ldg(a.m1 + (int64_t)i1 * W + P);
                 dg2 = TWO ? __ldg(a.m1 + (int64_t)i1 * W + P) : 0.0;
             }
@@ -320,6 +322,10 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                         const double rr = pfb[(ty * E + e) * T3 + tx] - v;
                         a.y[idx] = rr;
                         dsum = fma(rr, rr, dsum);
+                    } else if (EPI == POMS_EPI_AXPY) {
+                        const double w_ = a.omega * v;
+                        a.y[idx] = pfb[(ty * E + e) * T3 + tx] + w_;
+                        dsum = fma(w_, w_, dsum);
                     } else {
                         const double dg = TWO ? dg1 * dA[e] + dg2 * dB[e] : dg1 * dA[e];
                         const double dr = a.omega * (pfb[(ty * E + e) * T3 + tx] - v) / dg;
@@ -421,7 +427,7 @@ kron_matvec3d_wp_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         }
     }
     double dA[E], dB[E];
-    if (EPI >= POMS_EPI_JACOBI) {
+    if (EPI == POMS_EPI_JACOBI || EPI == POMS_EPI_DINV) {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int i2 = i2_0 + ty * E + e;
@@ -615,7 +621,7 @@ kron_matvec3d_wp_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         if (emit) {
             const int64_t o = (int64_t)i1 * a.pld + poff;
             double dg1 = 0.0, dg2 = 0.0;
-            if (EPI >= POMS_EPI_JACOBI) {
+            if (EPI == POMS_EPI_JACOBI || EPI == POMS_EPI_DINV) {
                 dg1 = TWO ? __ldg(a.k1 + (int64_t)i1 * W + P) : __ldg(a.m1 + (int64_t)i1 * W + P);
                 dg2 = TWO ? __ldg(a.m1 + (int64_t)i1 * W + P) : 0.0;
             }
@@ -631,6 +637,10 @@ kron_matvec3d_wp_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
                         const double rr = pfb[pslot + e * T3] - v;
                         a.y[idx] = rr;
                         dsum = fma(rr, rr, dsum);
+                    } else if (EPI == POMS_EPI_AXPY) {
+                        const double w_ = a.omega * v;
+                        a.y[idx] = pfb[pslot + e * T3] + w_;
+                        dsum = fma(w_, w_, dsum);
                     } else {
                         const double dg = TWO ? dg1 * dA[e] + dg2 * dB[e] : dg1 * dA[e];
                         const double dr = a.omega * (pfb[pslot + e * T3] - v) / dg;
@@ -704,6 +714,7 @@ static int launch_mv3_tma_epi(const CUtensorMap& tm, const MV3T& g, int epi, dim
         case POMS_EPI_RESID: return launch_mv3_tma_inst<P, FORM, POMS_EPI_RESID>(tm, g, grid, st);
         case POMS_EPI_JACOBI: return launch_mv3_tma_inst<P, FORM, POMS_EPI_JACOBI>(tm, g, grid, st);
         case POMS_EPI_DINV: return launch_mv3_tma_inst<P, FORM, POMS_EPI_DINV>(tm, g, grid, st);
+        case POMS_EPI_AXPY: return launch_mv3_tma_inst<P, FORM, POMS_EPI_AXPY>(tm, g, grid, st);
         default: return bad_arg(19, "epilogue");
     }
 }

@@ -27,7 +27,7 @@ from . import bsplines as bs
 from . import profiling
 from .multilevels import knots_to_insert
 from .stencil import (StencilVectorSpace, StencilVector, KronSumMatrix, DeviceContext,
-                      _stream, EPI_STORE, EPI_RESID, EPI_DINV)
+                      _stream, EPI_STORE, EPI_RESID, EPI_DINV, EPI_AXPY)
 from .kron_product import BandLU, kron_solve_bnd, kron_solve_bnd_update
 from . import solvers
 
@@ -402,7 +402,9 @@ class Hierarchy:
             lv.distributed = (slab is not None and slab.size > 1
                               and (not self.levels or self.levels[-1].distributed)
                               and (Ns[0] + p) >= slab.size * max(2 * p + 2, min_planes))
-            lv.V = StencilVectorSpace([n + p for n in Ns], [p] * self.ndim,
+            # ghost planes along the slab axis: p for the operator, 2q for the F2 pass of glt_poly
+            gp = max(p, 2 * max(p - 1, 1)) if smoother == "glt_poly" else p
+            lv.V = StencilVectorSpace([n + p for n in Ns], [gp] + [p] * (self.ndim - 1),
                                       [False] * self.ndim, device=self.device,
                                       slab=slab if lv.distributed else None)
             self.levels.append(lv)
@@ -440,10 +442,27 @@ class Hierarchy:
                 muK = _gen_eig_max(bs.pad_band(Kb, A.P), bs.pad_band(lv.glt_bands[a], A.P))
                 best = max(best, muK * float(np.prod([muM[c] for c in range(d) if c != a])))
             lv.lmax = self.safety * best
+        elif self.smoother == "glt_poly":
+            # B^-1 ~ q(T) (x) .. (x) q(T): degree-3 Chebyshev approximation of the GLT solve, applied
+            # as TWO fused Kronecker band passes (F1: half-bandwidth q, F2: 2q) instead of 2d
+            # sequential triangular sweeps.  Same lambda_max formula as 'glt' (B is spectrally within
+            # (1 +- 0.1)^d of the exact Kronecker solve).
+            q = max(2 * p - 1, 1)
+            lv.glt_bands = [bs.glt_band(p, n, degree=q) for n in A.npts]
+            F = [bs.poly_inverse_factors(b_, 3) for b_ in lv.glt_bands]
+            lv.S1 = KronSumMatrix([f[0] for f in F])
+            lv.S2 = KronSumMatrix([f[1] for f in F])
+            muM = [_gen_eig_max(A.mass_bands[a], lv.glt_bands[a]) for a in range(d)]
+            best = 0.0
+            for a in range(d):
+                Kb = A.Ks[a] + (A.mass_bands[a] if a != d - 1 else 0.0)
+                muK = _gen_eig_max(bs.pad_band(Kb, A.P), bs.pad_band(lv.glt_bands[a], A.P))
+                best = max(best, muK * float(np.prod([muM[c] for c in range(d) if c != a])))
+            lv.lmax = self.safety * best    # q(t) t = 0.9 at the high-frequency end of the symbol
         elif self.smoother == "jacobi":
             lv.lmax = self.safety * self._power_lmax_jacobi(lv)
         else:
-            raise ValueError("smoother must be 'glt' or 'jacobi'")
+            raise ValueError("smoother must be 'glt', 'glt_poly' or 'jacobi'")
         lv.lmin = lv.lmax / self.ratio
 
     def _power_lmax_jacobi(self, lv, iters=30):
@@ -475,6 +494,21 @@ class Hierarchy:
         delta = 0.5 * (lv.lmax - lv.lmin)
         sigma = theta / delta
         rho = 1.0 / sigma
+        if self.smoother == "glt_poly":
+            # nu Richardson steps x <- x + (1/theta) S2 S1 (b - A x): three fused Kronecker passes
+            t1 = StencilVector(V, zero=False)
+            for k in range(self.nu):
+                if k == 0 and zero_guess:
+                    src = b
+                else:
+                    r = StencilVector(V, zero=False)
+                    A.apply(x, r, EPI_RESID, b=b)
+                    src = r
+                lv.S1.apply(src, t1, EPI_STORE)
+                # in place: the epilogue reads x[i] and writes x[i] from the same thread, and the
+                # mat-vec input is t1, so no other thread reads x
+                lv.S2.apply(t1, x, EPI_AXPY, b=x, omega=1.0 / theta)
+            return x
         if self.smoother == "glt" and self.nu == 1 and all(lu.nopiv for lu in lv.glt_lu):
             # one step: x <- x + (1/theta) B^-1 (b - A x); the update is fused into the last line
             # solve (d = c1*d + c2*z with c1 = 0, so x + d == x + c2*z)

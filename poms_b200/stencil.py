@@ -22,7 +22,7 @@ from . import bsplines as bs
 from . import profiling
 
 FORM_SINGLE, FORM_SUM = 0, 1
-EPI_STORE, EPI_RESID, EPI_JACOBI, EPI_DINV = 0, 1, 2, 3
+EPI_STORE, EPI_RESID, EPI_JACOBI, EPI_DINV, EPI_AXPY = 0, 1, 2, 3, 4
 
 
 def _stream():
