@@ -12,6 +12,7 @@
 // otherwise from shared / global memory (CTA-uniform branch).
 #pragma once
 #include <cuda.h>
+#include <type_traits>
 
 struct MV3T {
     MV3 a;
@@ -155,53 +156,61 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             }
         }
     }
-    // per-thread offset of its first output point inside a plane
+    // per-thread offset of its first output point inside a plane, validity mask of its E points
     const int64_t poff = (int64_t)(i2_0 + ty * E) * a.ld + i3;
-    unsigned phase_bits = 0;
-    int u = 0, st = 0;
-#pragma unroll 1
-    for (int j1 = start; j1 < end; ++j1) {
-        const int t = j1 - start;
-        const bool have = valid(j1);
-        const int i1 = j1 - P;
-        const bool emit = (i1 >= c_lo && i1 < c_hi);
-        // Prefetch what the epilogue of the output plane completed by this input plane needs, with
-        // cp.async into per-thread shared slots: no registers are held across stages 1-3 (keeping
-        // them in registers made ptxas spill and stall on the load right away).
-        constexpr bool NEED_B = (EPI != POMS_EPI_STORE);
-        const bool need_x = (EPI == POMS_EPI_STORE && a.dot_out) || EPI == POMS_EPI_JACOBI;
-        if (emit && v3) {
-            const int64_t o = (int64_t)i1 * a.pld + poff;
+    unsigned okmask = 0;
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                if ((i2_0 + ty * E + e) < a.n2) {
-                    if (NEED_B) cp_async8(pfb + (ty * E + e) * T3 + tx, a.b + o + (int64_t)e * a.ld);
-                    if (need_x) cp_async8(pfx + (ty * E + e) * T3 + tx, a.x + o + (int64_t)e * a.ld);
+    for (int e = 0; e < E; ++e)
+        if (v3 && (i2_0 + ty * E + e) < a.n2) okmask |= 1u << e;
+    const int pslot = (ty * E) * T3 + tx;
+    constexpr bool NEED_B = (EPI != POMS_EPI_STORE);
+    const bool need_x = (EPI == POMS_EPI_STORE && a.dot_out) || EPI == POMS_EPI_JACOBI;
+    // output / rhs pointers of the NEXT plane to be emitted (planes are emitted in order)
+    int64_t eoff = (int64_t)c_lo * a.pld + poff;
+    unsigned phase_bits = 0;
+    int u = 0, st = 0, t = 0;
+
+    // One plane of the march.  STEADY = the plane is valid, completes an owned output plane, lies in
+    // the Toeplitz-interior range of axis 1 and the prefetched plane exists: no checks are compiled.
+    auto plane = [&](const int j1, auto steady_tag) {
+        constexpr bool STEADY = decltype(steady_tag)::value;
+        const bool have = STEADY ? true : valid(j1);
+        const int i1 = j1 - P;
+        const bool emit = STEADY ? true : (i1 >= c_lo && i1 < c_hi);
+        if (NEED_B || need_x) {
+            if (emit) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if (okmask & (1u << e)) {
+                        if (NEED_B) cp_async8(pfb + pslot + e * T3, a.b + eoff + (int64_t)e * a.ld);
+                        if (need_x) cp_async8(pfx + pslot + e * T3, a.x + eoff + (int64_t)e * a.ld);
+                    }
                 }
             }
+            cp_async_commit();
         }
-        cp_async_commit();
         double* const sub = su + (t & 1) * C::SU_DOUBLES;
         double* const svb = sv + (t & 1) * C::SU_DOUBLES;
         if (have) {
             mbar_wait(mbar + st, (phase_bits >> st) & 1u);
             phase_bits ^= (1u << st);
-            const double* const sx = ring + (size_t)st * (C::STAGE_BYTES / 8);
+            const double* const sx = ring + (size_t)st * (C::STAGE_BYTES / 8) + 2 * lane;
             // ---- stage 1: band pass along axis 3; lane = pair of output columns ----
+            if (toep3) {
 #pragma unroll 1
-            for (int r = wid; r < R2; r += 8) {
-                double xr[NX];
-                const double2* src = reinterpret_cast<const double2*>(sx + r * C3 + 2 * lane);
+                for (int r = wid; r < R2; r += 8) {
+                    double xr[NX];
+                    const double2* src = reinterpret_cast<const double2*>(sx + r * C3);
 #pragma unroll
-                for (int q = 0; q < NX / 2; ++q) {
-                    const double2 v2 = src[q];
-                    xr[2 * q] = v2.x;
-                    xr[2 * q + 1] = v2.y;
-                }
-                double ua = 0.0, ub = 0.0, va = 0.0, vb = 0.0;
-                if (toep3) {
+                    for (int q = 0; q < NX / 2; ++q) {
+                        const double2 v2 = src[q];
+                        xr[2 * q] = v2.x;
+                        xr[2 * q + 1] = v2.y;
+                    }
+                    double ua = g.t3m[0] * xr[0], ub = g.t3m[0] * xr[1];
+                    double va = TWO ? g.t3k[0] * xr[0] : 0.0, vb = TWO ? g.t3k[0] * xr[1] : 0.0;
 #pragma unroll
-                    for (int k = 0; k < W; ++k) {
+                    for (int k = 1; k < W; ++k) {
                         ua = fma(g.t3m[k], xr[k], ua);
                         ub = fma(g.t3m[k], xr[k + 1], ub);
                         if (TWO) {
@@ -209,8 +218,22 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                             vb = fma(g.t3k[k], xr[k + 1], vb);
                         }
                     }
-                } else {  // boundary columns: coefficients of these two rows of M3 / K3
-                    const bool oka = ca >= 0 && ca < a.n3, okb = cb >= 0 && cb < a.n3;
+                    *reinterpret_cast<double2*>(sub + r * T3 + 2 * lane) = make_double2(ua, ub);
+                    if (TWO) *reinterpret_cast<double2*>(svb + r * T3 + 2 * lane) = make_double2(va, vb);
+                }
+            } else {  // boundary columns: coefficients of these two rows of M3 / K3 from memory
+                const bool oka = ca >= 0 && ca < a.n3, okb = cb >= 0 && cb < a.n3;
+#pragma unroll 1
+                for (int r = wid; r < R2; r += 8) {
+                    double xr[NX];
+                    const double2* src = reinterpret_cast<const double2*>(sx + r * C3);
+#pragma unroll
+                    for (int q = 0; q < NX / 2; ++q) {
+                        const double2 v2 = src[q];
+                        xr[2 * q] = v2.x;
+                        xr[2 * q + 1] = v2.y;
+                    }
+                    double ua = 0.0, ub = 0.0, va = 0.0, vb = 0.0;
 #pragma unroll
                     for (int k = 0; k < W; ++k) {
                         const double ma = oka ? __ldg(a.m3 + (int64_t)ca * W + k) : 0.0;
@@ -224,14 +247,14 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                             vb = fma(kb, xr[k + 1], vb);
                         }
                     }
+                    *reinterpret_cast<double2*>(sub + r * T3 + 2 * lane) = make_double2(ua, ub);
+                    if (TWO) *reinterpret_cast<double2*>(svb + r * T3 + 2 * lane) = make_double2(va, vb);
                 }
-                *reinterpret_cast<double2*>(sub + r * T3 + 2 * lane) = make_double2(ua, ub);
-                if (TWO) *reinterpret_cast<double2*>(svb + r * T3 + 2 * lane) = make_double2(va, vb);
             }
         }
         __syncthreads();
         // ---- producer: plane j1+PD into the slot of plane j1-1 (every thread is past its stage 1)
-        if (tid == 0 && j1 + PD < end && valid(j1 + PD)) {
+        if (tid == 0 && (STEADY || (j1 + PD < end && valid(j1 + PD)))) {
             const int sn = (st + PD) % NST;
             mbar_expect_tx(mbar + sn, R2 * C3 * 8);
             tma_load_3d(ring + (size_t)sn * (C::STAGE_BYTES / 8), &tmap, i3_0 - P, i2_0 - P,
@@ -253,9 +276,9 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                     for (int e = 0; e < E; ++e) {
                         const int k = r - e;
                         if (k >= 0 && k < W) {
-                            ta[e] = fma(g.t2m[k], uv, ta[e]);
+                            ta[e] = (k == 0) ? g.t2m[0] * uv : fma(g.t2m[k], uv, ta[e]);
                             if (TWO) {
-                                tb[e] = fma(g.t2k[k], uv, tb[e]);
+                                tb[e] = (k == 0) ? g.t2k[0] * uv : fma(g.t2k[k], uv, tb[e]);
                                 tb[e] = fma(g.t2m[k], vv, tb[e]);
                             }
                         }
@@ -282,7 +305,7 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             }
         }
         // ---- stage 3: rotating axis-1 partial sums ----
-        const bool toep1 = have && (j1 - P >= g.lo1) && (j1 + P < g.hi1);
+        const bool toep1 = STEADY ? true : (have && (j1 - P >= g.lo1) && (j1 + P < g.hi1));
         if (toep1) {
             rot_scatter<W, E, TWO>(u, acc, ta, tb, *(const double(*)[W])(TWO ? g.t1k : g.t1m), *(const double(*)[W]) g.t1m, vout);
         } else {
@@ -302,42 +325,56 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             rot_scatter<W, E, TWO>(u, acc, ta, tb, c1k, c1m, vout);
         }
         // ---- epilogue: output plane i1 = j1 - P ----
-        cp_async_wait<0>();
+        if (NEED_B || need_x) cp_async_wait<0>();
         if (emit) {
-            const int64_t o = (int64_t)i1 * a.pld + poff;
             double dg1 = 0.0, dg2 = 0.0;
             if (EPI == POMS_EPI_JACOBI || EPI == POMS_EPI_DINV) {
                 dg1 = TWO ? __ldg(a.k1 + (int64_t)i1 * W + P) : __ldg(a.m1 + (int64_t)i1 * W + P);
                 dg2 = TWO ? __ldg(a.m1 + (int64_t)i1 * W + P) : 0.0;
             }
+            double* const yp = a.y + eoff;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                if (v3 && (i2_0 + ty * E + e) < a.n2) {
-                    const int64_t idx = o + (int64_t)e * a.ld;
+                if (okmask & (1u << e)) {
                     const double v = vout[e];
                     if (EPI == POMS_EPI_STORE) {
-                        a.y[idx] = v;
-                        if (a.dot_out) dsum = fma(pfx[(ty * E + e) * T3 + tx], v, dsum);
+                        yp[(int64_t)e * a.ld] = v;
+                        if (need_x) dsum = fma(pfx[pslot + e * T3], v, dsum);
                     } else if (EPI == POMS_EPI_RESID) {
-                        const double rr = pfb[(ty * E + e) * T3 + tx] - v;
-                        a.y[idx] = rr;
+                        const double rr = pfb[pslot + e * T3] - v;
+                        yp[(int64_t)e * a.ld] = rr;
                         dsum = fma(rr, rr, dsum);
                     } else if (EPI == POMS_EPI_AXPY) {
                         const double w_ = a.omega * v;
-                        a.y[idx] = pfb[(ty * E + e) * T3 + tx] + w_;
+                        yp[(int64_t)e * a.ld] = pfb[pslot + e * T3] + w_;
                         dsum = fma(w_, w_, dsum);
                     } else {
                         const double dg = TWO ? dg1 * dA[e] + dg2 * dB[e] : dg1 * dA[e];
-                        const double dr = a.omega * (pfb[(ty * E + e) * T3 + tx] - v) / dg;
-                        a.y[idx] = (EPI == POMS_EPI_JACOBI) ? pfx[(ty * E + e) * T3 + tx] + dr : dr;
+                        const double dr = a.omega * (pfb[pslot + e * T3] - v) / dg;
+                        yp[(int64_t)e * a.ld] = (EPI == POMS_EPI_JACOBI) ? pfx[pslot + e * T3] + dr : dr;
                         dsum = fma(dr, dr, dsum);
                     }
                 }
             }
+            eoff += a.pld;
         }
         u = (u + 1 == W) ? 0 : u + 1;
         st = (st + 1 == NST) ? 0 : st + 1;
-    }
+        ++t;
+    };
+
+    // steady range of input planes: valid, emitting, Toeplitz in axis 1, and plane j1+PD loadable
+    int s_lo = max(max(start, -a.glo), max(c_lo + P, g.lo1 + P));
+    int s_hi = min(min(end, a.n1 + a.ghi), min(c_hi + P, g.hi1 - P));
+    s_hi = min(s_hi, min(end, a.n1 + a.ghi) - PD);
+    if (s_hi < s_lo) s_hi = s_lo = start;
+    int j1 = start;
+#pragma unroll 1
+    for (; j1 < s_lo; ++j1) plane(j1, std::false_type{});
+#pragma unroll 1
+    for (; j1 < s_hi; ++j1) plane(j1, std::true_type{});
+#pragma unroll 1
+    for (; j1 < end; ++j1) plane(j1, std::false_type{});
     if (a.dot_out) {
         const double tot = block_sum(dsum, red);
         const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
