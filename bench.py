@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--smoother", default="auto", choices=["auto", "glt", "glt_poly", "jacobi"])
     ap.add_argument("--nu", type=int, default=1)
+    ap.add_argument("--nc", type=int, default=0, help="coarsest grid (elements per axis); 0 = auto")
     ap.add_argument("--rhs", default="auto", choices=["auto", "ones", "manufactured"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
@@ -209,8 +210,11 @@ def main():
     # weak scaling: the domain grows with the grid, [0, G] x [0,1]^(d-1), so the elements stay cubes
     # (keeping [0,1]^d would make the global problem anisotropic and change the iteration count)
     lengths = [float(world)] + [1.0] * (ndim - 1)
+    # coarsest level: solved exactly by fast diagonalisation, so it need not be tiny; stopping at 32
+    # elements per axis in 3-D saves two levels of launch-latency-bound kernels per V-cycle
+    Nc = args.nc if args.nc > 0 else (32 if ndim == 3 else 8)
     h = Hierarchy(p, Ns, device=dev, smoother=args.smoother, nu=args.nu, slab=slab,
-                  lengths=lengths)
+                  lengths=lengths, Nc=Nc)
     V = h.levels[0].V
     dof_global = int(np.prod(V.npts))
     b = StencilVector(V)
@@ -340,6 +344,7 @@ def main():
                              % (args.nu, args.nu, args.smoother),
                    "rhs": "b = 1 (mg_jac.py:59-61)" if rhs == "ones" else
                           "b = A x0, x0[i] = sum(i_a) + 1 (tests/test_pcg.py:52-58)",
+                   "coarsest_elements": Nc,
                    "iterations": info["niter"], "restarts": info.get("restarts", 0),
                    "levels": len(h.levels),
                    "rel_residual_reported": info["res_norm"] / info["res_norm0"],

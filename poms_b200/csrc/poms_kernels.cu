@@ -368,7 +368,9 @@ static int pick_chunk(int n1, int64_t tiles, int p) {
     int64_t nch = (want + tiles - 1) / tiles;
     if (nch < 1) nch = 1;
     int chunk = (int)((n1 + nch - 1) / nch);
-    const int min_chunk = 8 * (2 * p);  // <= 12.5% redundant planes
+    // big grids: <= 12.5 % redundant halo planes; small (coarse-level) grids are latency bound, so
+    // more, shorter CTAs win even at 50 % redundancy
+    const int min_chunk = (tiles >= 148 ? 8 : 2) * (2 * p);
     if (chunk < min_chunk) chunk = min_chunk;
     if (chunk > n1) chunk = n1;
     return chunk;
