@@ -85,6 +85,8 @@ void poms_set_force_generic(int flag);
 /* 3-D TMA kernel variant: 0 = block-synchronous (default; 1.51 ms at 512^3), 1 = warp-private strips
  * (1.64 ms; kept for A-B timing) */
 void poms_set_matvec3d_variant(int v);
+/* A/B timing only: fix the axis-1 chunk (planes per CTA) of the 3-D mat-vec; 0 = automatic. */
+void poms_set_matvec3d_chunk(int chunk);
 
 /*
  * Full (non-separable) 2-D stencil mat-vec: y[i1,i2] = sum_{k1,k2} S[i1,i2,k1,k2] x[i1+k1-p1,i2+k2-p2]

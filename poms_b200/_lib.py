@@ -22,6 +22,7 @@ _PROTOS = {
                                         _vp, _vp]),
     "poms_set_force_generic": (None, [_i]),
     "poms_set_matvec3d_variant": (None, [_i]),
+    "poms_set_matvec3d_chunk": (None, [_i]),
     "poms_stencil_matvec_2d": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _l, _i, _i, _i, _i,
                                         _i, _d, _vp, _vp, _vp]),
     "poms_cg_update": (C.c_int, [_vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp]),

@@ -362,15 +362,20 @@ static int launch_mv3(const MV3& a, int form, int epi, dim3 grid, cudaStream_t s
     return bad_arg(12, "form");
 }
 
+static int g_chunk_override = 0;   // > 0: fixed axis-1 chunk (A/B timing only)
+extern "C" void poms_set_matvec3d_chunk(int c) { g_chunk_override = c; }
 static int pick_chunk(int n1, int64_t tiles, int p) {
-    // enough CTAs for ~4 waves of 148 SMs x 2 CTAs, but keep the 2p halo planes amortised
-    const int64_t want = 148 * 2 * 4;
+    if (g_chunk_override > 0) return g_chunk_override < n1 ? g_chunk_override : n1;
+    // enough CTAs for ~8 waves of 148 SMs x 2 CTAs on big grids (boundary and ragged tiles are cheaper
+    // than interior ones, so short CTAs balance better: 65 planes measured 3 % faster than 129 at
+    // 515^3), ~4 waves on small ones, but keep the 2p halo planes amortised:
+    // big grids <= 12.5 % redundant halo planes; coarse-level grids are latency bound, so more,
+    // shorter CTAs win even at 50-100 % redundancy (measured sweep: profiles/r01_ab_chunk_sweep.txt)
+    const int64_t want = 148 * 2 * (tiles >= 148 ? 8 : 4);
     int64_t nch = (want + tiles - 1) / tiles;
     if (nch < 1) nch = 1;
     int chunk = (int)((n1 + nch - 1) / nch);
-    // big grids: <= 12.5 % redundant halo planes; small (coarse-level) grids are latency bound, so
-    // more, shorter CTAs win even at 50 % redundancy
-    const int min_chunk = (tiles >= 148 ? 8 : 2) * (2 * p);
+    const int min_chunk = (tiles >= 148 ? 8 : tiles >= 20 ? 2 : 1) * (2 * p);
     if (chunk < min_chunk) chunk = min_chunk;
     if (chunk > n1) chunk = n1;
     return chunk;

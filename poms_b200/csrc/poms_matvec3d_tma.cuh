@@ -101,10 +101,18 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     const int c_hi = min(a.n1, c_lo + a.chunk);
     const int i3 = i3_0 + tx;
     const bool v3 = i3 >= 0 && i3 < a.n3;
-    const bool toep2 = (i2_0 >= g.lo2) && (i2_0 + T2 <= g.hi2);
+    // axis-2 coefficients: Toeplitz per thread (warp-uniform: a warp holds ONE ty), table otherwise
+    const bool toep2_cta = (i2_0 >= g.lo2) && (i2_0 + T2 <= g.hi2);
+    const bool toep2 = (i2_0 + ty * E >= g.lo2) && (i2_0 + ty * E + E <= g.hi2);
+    // rows of the halo'd tile that feed an output row inside the domain (ragged last tile row)
+    const int r_hi = min(R2, a.n2 - i2_0 + 2 * P);
     // stage-1 columns of this lane and whether both are Toeplitz-interior rows of M3 / K3
-    const int ca = i3_0 + 2 * lane, cb = ca + 1;
-    const bool toep3 = (ca >= g.lo3) && (cb < g.hi3);
+    // pairs [0, qb) intersect the domain; pairs [tl, th) of them are Toeplitz, the other nb are not
+    const int qb = min(T3 / 2, (a.n3 - i3_0 + 1) >> 1);
+    const int tl = min(max((g.lo3 - i3_0 + 1) >> 1, 0), qb);
+    const int th = min(max((g.hi3 - i3_0) >> 1, tl), qb);
+    const int nb = tl + (qb - th);
+    const bool toep3 = lane >= tl && lane < th;
 
     if (tid == 0) {
 #pragma unroll
@@ -112,7 +120,7 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
-    if (!toep2) {
+    if (!toep2_cta) {
         for (int t = tid; t < T2 * W; t += blockDim.x) {
             const int r = t / W, k = t - r * W, i2 = i2_0 + r;
             c2m[t] = i2 < a.n2 ? a.m2[(int64_t)i2 * W + k] : 0.0;
@@ -163,6 +171,8 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     for (int e = 0; e < E; ++e)
         if (v3 && (i2_0 + ty * E + e) < a.n2) okmask |= 1u << e;
     const int pslot = (ty * E) * T3 + tx;
+    // warps whose 32 columns x E rows lie outside the domain (ragged last tiles) skip stages 2 and 3
+    const bool wlive = __ballot_sync(0xffffffffu, okmask != 0) != 0;
     constexpr bool NEED_B = (EPI != POMS_EPI_STORE);
     const bool need_x = (EPI == POMS_EPI_STORE && a.dot_out) || EPI == POMS_EPI_JACOBI;
     // output / rhs pointers of the NEXT plane to be emitted (planes are emitted in order)
@@ -197,8 +207,8 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             const double* const sx = ring + (size_t)st * (C::STAGE_BYTES / 8) + 2 * lane;
             // ---- stage 1: band pass along axis 3; lane = pair of output columns ----
             if (toep3) {
-#pragma unroll 1
-                for (int r = wid; r < R2; r += 8) {
+                // one row of the halo'd tile per warp and round; `row1` is the body for one row
+                auto row1 = [&](const int r) {
                     double xr[NX];
                     const double2* src = reinterpret_cast<const double2*>(sx + r * C3);
 #pragma unroll
@@ -220,36 +230,44 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                     }
                     *reinterpret_cast<double2*>(sub + r * T3 + 2 * lane) = make_double2(ua, ub);
                     if (TWO) *reinterpret_cast<double2*>(svb + r * T3 + 2 * lane) = make_double2(va, vb);
-                }
-            } else {  // boundary columns: coefficients of these two rows of M3 / K3 from memory
-                const bool oka = ca >= 0 && ca < a.n3, okb = cb >= 0 && cb < a.n3;
+                };
 #pragma unroll 1
-                for (int r = wid; r < R2; r += 8) {
-                    double xr[NX];
-                    const double2* src = reinterpret_cast<const double2*>(sx + r * C3);
+                for (int r = wid; r < r_hi; r += 8) row1(r);
+            }
+            // ---- stage 1 fix-up: column pairs holding a non-Toeplitz (boundary) row of M3 / K3.  They
+            // are the first `tl` and the last `qb - th` pairs of the tile (<= p+1 pairs per domain end),
+            // so the R2 x nb (row, pair) items are spread over the whole CTA: one round in a boundary
+            // tile, nothing in an interior one; coefficients come from global memory (L1 resident).
+            for (int it = tid; it < r_hi * nb; it += 256) {
+                const int r = it / nb, q = it - r * nb;
+                const int pr = q < tl ? q : th + (q - tl);
+                const int fa = i3_0 + 2 * pr, fb = fa + 1;
+                const bool oka = fa >= 0 && fa < a.n3, okb = fb >= 0 && fb < a.n3;
+                double xr[NX];
+                const double2* src = reinterpret_cast<const double2*>(
+                    ring + (size_t)st * (C::STAGE_BYTES / 8) + r * C3 + 2 * pr);
 #pragma unroll
-                    for (int q = 0; q < NX / 2; ++q) {
-                        const double2 v2 = src[q];
-                        xr[2 * q] = v2.x;
-                        xr[2 * q + 1] = v2.y;
-                    }
-                    double ua = 0.0, ub = 0.0, va = 0.0, vb = 0.0;
-#pragma unroll
-                    for (int k = 0; k < W; ++k) {
-                        const double ma = oka ? __ldg(a.m3 + (int64_t)ca * W + k) : 0.0;
-                        const double mb = okb ? __ldg(a.m3 + (int64_t)cb * W + k) : 0.0;
-                        ua = fma(ma, xr[k], ua);
-                        ub = fma(mb, xr[k + 1], ub);
-                        if (TWO) {
-                            const double ka = oka ? __ldg(a.k3 + (int64_t)ca * W + k) : 0.0;
-                            const double kb = okb ? __ldg(a.k3 + (int64_t)cb * W + k) : 0.0;
-                            va = fma(ka, xr[k], va);
-                            vb = fma(kb, xr[k + 1], vb);
-                        }
-                    }
-                    *reinterpret_cast<double2*>(sub + r * T3 + 2 * lane) = make_double2(ua, ub);
-                    if (TWO) *reinterpret_cast<double2*>(svb + r * T3 + 2 * lane) = make_double2(va, vb);
+                for (int q2 = 0; q2 < NX / 2; ++q2) {
+                    const double2 v2 = src[q2];
+                    xr[2 * q2] = v2.x;
+                    xr[2 * q2 + 1] = v2.y;
                 }
+                double ua = 0.0, ub = 0.0, va = 0.0, vb = 0.0;
+#pragma unroll
+                for (int k = 0; k < W; ++k) {
+                    const double ma = oka ? __ldg(a.m3 + (int64_t)fa * W + k) : 0.0;
+                    const double mb = okb ? __ldg(a.m3 + (int64_t)fb * W + k) : 0.0;
+                    ua = fma(ma, xr[k], ua);
+                    ub = fma(mb, xr[k + 1], ub);
+                    if (TWO) {
+                        const double ka = oka ? __ldg(a.k3 + (int64_t)fa * W + k) : 0.0;
+                        const double kb = okb ? __ldg(a.k3 + (int64_t)fb * W + k) : 0.0;
+                        va = fma(ka, xr[k], va);
+                        vb = fma(kb, xr[k + 1], vb);
+                    }
+                }
+                *reinterpret_cast<double2*>(sub + r * T3 + 2 * pr) = make_double2(ua, ub);
+                if (TWO) *reinterpret_cast<double2*>(svb + r * T3 + 2 * pr) = make_double2(va, vb);
             }
         }
         __syncthreads();
@@ -263,6 +281,7 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
         double ta[E], tb[E], vout[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) ta[e] = tb[e] = 0.0;
+        if (wlive) {
         if (have) {
             // ---- stage 2: band pass along axis 2, scatter form (no register window) ----
             const double* const up = sub + (ty * E) * T3 + tx;
@@ -358,6 +377,7 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
             }
             eoff += a.pld;
         }
+        }  // wlive
         u = (u + 1 == W) ? 0 : u + 1;
         st = (st + 1 == NST) ? 0 : st + 1;
         ++t;
