@@ -131,6 +131,24 @@ def cpu_sample_size(ndim):
     return 128 if ndim == 3 else 1024
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """Keep the real stdout for the ONE JSON line and send everything else a library may print
+    there (NCCL's version banner, numba / torch notices) to stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU algorithm on the host cores (oracle port)."""
     if rank != 0:
@@ -159,7 +177,7 @@ def run_reference(args, rank):
                                    % (Ns, ndim, label)},
         "e2e": {"value": v, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 def main():
@@ -176,6 +194,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -197,6 +216,8 @@ def main():
     slab = None
     if world > 1:
         from poms_b200.dist import Slab
+        # NCCL writes its version banner to stdout when NCCL_DEBUG is set; stdout carries the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         slab = Slab(dist.group.WORLD, dev)
     ndim, p, N, desc = CONFIGS[args.config]
@@ -212,9 +233,12 @@ def main():
     lengths = [float(world)] + [1.0] * (ndim - 1)
     # coarsest level: solved exactly by fast diagonalisation, so it need not be tiny; stopping at 32
     # elements per axis in 3-D saves two levels of launch-latency-bound kernels per V-cycle
-    Nc = args.nc if args.nc > 0 else (32 if ndim == 3 else 8)
+    # With slabs the coarsest level must be small enough to be replicated (< 32 planes per rank), hence
+    # 16.  Levels are coarsened uniformly (all axes together): the elongated weak-scaling domain then
+    # has the same element shapes and the same number of levels as the single-GPU cube.
+    Nc = args.nc if args.nc > 0 else ((32 if world == 1 else 16) if ndim == 3 else 8)
     h = Hierarchy(p, Ns, device=dev, smoother=args.smoother, nu=args.nu, slab=slab,
-                  lengths=lengths, Nc=Nc)
+                  lengths=lengths, Nc=Nc, coarsen="uniform")
     V = h.levels[0].V
     dof_global = int(np.prod(V.npts))
     b = StencilVector(V)
@@ -373,7 +397,7 @@ def main():
                                 "sample": "%d^%d elements (%d DOF), one full MG-PCG solve to 1e-10, "
                                           "%s, %d iterations, %.1f s"
                                           % (Nc, ndim, dofc, label, infoc["niter"], dtc)}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -42,7 +42,7 @@ int64_t poms_launch_count(void);
 #define POMS_EPI_RESID  1  /* y = b - v                  ; dot += y*y   (r.r)                */
 #define POMS_EPI_JACOBI 2  /* y = x + om*(b - v)/diag(A) ; dot += dr*dr (damped Jacobi sweep) */
 #define POMS_EPI_DINV   3  /* y = om*(b - v)/diag(A)     ; dot += y*y   (Jacobi-preconditioned residual) */
-#define POMS_EPI_AXPY   4  /* y = b + om*v               ; dot += (om*v)^2 (EXTENSION: smoother update) */
+#define POMS_EPI_AXPY   4  /* y = b + om*v (b NULL: om*v) ; dot += (om*v)^2 (EXTENSION: smoother update) */
 
 /*
  * Kronecker-structured banded mat-vec, one fused pass (16 B/DOF algorithmic).
@@ -82,9 +82,6 @@ int poms_kron_matvec_3d_ex(const double* x, double* y, const double* b,
                            int epilogue, double omega, double* dot_out, void* ws, void* stream,
                            const double* toep_host, const int* toep_rng_host);
 void poms_set_force_generic(int flag);
-/* 3-D TMA kernel variant: 0 = block-synchronous (default; 1.51 ms at 512^3), 1 = warp-private strips
- * (1.64 ms; kept for A-B timing) */
-void poms_set_matvec3d_variant(int v);
 /* A/B timing only: fix the axis-1 chunk (planes per CTA) of the 3-D mat-vec; 0 = automatic. */
 void poms_set_matvec3d_chunk(int chunk);
 
@@ -182,6 +179,26 @@ int poms_axis_gather(const double* in, double* out, const int32_t* start, const 
                      int W, int n_in, int n_out, int64_t n_outer, int64_t so_in, int64_t sa_in,
                      int64_t so_out, int64_t sa_out, int64_t n_inner, int accumulate,
                      void* stream);
+
+/*
+ * Fused 3-D transfers (EXTENSION of the per-axis gathers above: same rows, one pass).
+ *   poms_restrict_3d: coarse = (R1 (x) R2 (x) R3) fine     -- R.dot of sources/mg_jac.py:94
+ *   poms_prolong_3d:  fine (+)= (P1 (x) P2 (x) P3) coarse  -- P.dot + correction, mg_jac.py:102,112
+ * sN, cN: device rows (start, coef) of axis N in the poms_axis_gather format, WN taps per row
+ * (<= 8); sN_host: host copies of the starts, checked against the kernels' static tile bounds (a
+ * negative status means the caller must use poms_axis_gather).  ld / pld: row and plane pitches.
+ */
+int poms_restrict_3d(const double* fine, double* coarse, int n1f, int n2f, int n3f, int64_t ldf,
+                     int64_t pldf, int n1c, int n2c, int n3c, int64_t ldc, int64_t pldc,
+                     const int32_t* s1, const double* c1, int W1, const int32_t* s2,
+                     const double* c2, int W2, const int32_t* s3, const double* c3, int W3,
+                     const int32_t* s1_host, const int32_t* s2_host, const int32_t* s3_host,
+                     void* stream);
+int poms_prolong_3d(const double* coarse, double* fine, int n1f, int n2f, int n3f, int64_t ldf,
+                    int64_t pldf, int n1c, int n2c, int n3c, int64_t ldc, int64_t pldc,
+                    const int32_t* s1, const double* c1, int W1, const int32_t* s2,
+                    const double* c2, int W2, const int32_t* s3, const double* c3, int W3,
+                    const int32_t* s2_host, const int32_t* s3_host, int accumulate, void* stream);
 
 /* y = Ainv x, dense row-major n x n (replicated coarse direct solve, sources/mg_jac.py:98-99) */
 int poms_dense_matvec(const double* Ainv, const double* x, double* y, int n, void* stream);

@@ -586,7 +586,8 @@ def _cheb_inverse_poly(lmin, lmax, degree):
 
 
 class MGHierarchy:
-    def __init__(self, p, N, Nc=8, smoother="glt", nu=1, ratio=4.0, safety=1.1, lengths=None):
+    def __init__(self, p, N, Nc=8, smoother="glt", nu=1, ratio=4.0, safety=1.1, lengths=None,
+                 coarsen="semi"):
         from scipy.linalg import eigh
         lengths = [1.0] * len(N) if lengths is None else [float(v) for v in lengths]
         self.p, self.smoother, self.nu, self.ratio = p, smoother, nu, ratio
@@ -598,6 +599,10 @@ class MGHierarchy:
             A, Mb, Kb = poisson_operator(p, knots)
             self.levels.append(dict(N=list(N), knots=knots, A=A, Mb=Mb, Kb=Kb))
             if all(n <= Nc for n in N):
+                break
+            # 'uniform': stop as soon as one axis cannot be halved (elements keep their shape on every
+            # level); 'semi': keep halving the longer axes alone
+            if coarsen == "uniform" and not all(n > Nc and n % 2 == 0 for n in N):
                 break
             nxt = [n // 2 if (n > Nc and n % 2 == 0) else n for n in N]
             if nxt == N:

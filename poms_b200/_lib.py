@@ -21,7 +21,6 @@ _PROTOS = {
                                         _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp,
                                         _vp, _vp]),
     "poms_set_force_generic": (None, [_i]),
-    "poms_set_matvec3d_variant": (None, [_i]),
     "poms_set_matvec3d_chunk": (None, [_i]),
     "poms_stencil_matvec_2d": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _l, _i, _i, _i, _i,
                                         _i, _d, _vp, _vp, _vp]),
@@ -43,6 +42,10 @@ _PROTOS = {
     "poms_axis_gather": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _l, _l, _l, _l, _l, _l,
                                   _i, _vp]),
     "poms_dense_matvec": (C.c_int, [_vp, _vp, _vp, _i, _vp]),
+    "poms_restrict_3d": (C.c_int, [_vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _l, _l,
+                                  _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "poms_prolong_3d": (C.c_int, [_vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _l, _l,
+                                 _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
 }
 
 EXPORTS = tuple(_PROTOS)

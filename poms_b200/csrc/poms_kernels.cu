@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256, 2) kron_matvec3d_kernel(MV3 a) {
                         dsum = fma(rr, rr, dsum);
                     } else if (EPI == POMS_EPI_AXPY) {
                         const double w_ = a.omega * v;
-                        a.y[idx] = a.b[idx] + w_;
+                        a.y[idx] = a.b ? a.b[idx] + w_ : w_;
                         dsum = fma(w_, w_, dsum);
                     } else {
                         double dg;
@@ -413,7 +413,7 @@ extern "C" int poms_kron_matvec_3d_ex(const double* x, double* y, const double* 
                                       const double* toep_host, const int* toep_rng_host) {
     if (!x) return bad_arg(1, "x");
     if (!y) return bad_arg(2, "y");
-    if (epilogue != POMS_EPI_STORE && !b) return bad_arg(3, "b required by epilogue");
+    if (epilogue != POMS_EPI_STORE && epilogue != POMS_EPI_AXPY && !b) return bad_arg(3, "b required by epilogue");
     if (n1 < 1 || n2 < 1 || n3 < 1) return bad_arg(4, "extent");
     if (ld < n3) return bad_arg(7, "ld");
     if (pld < ld * n2) return bad_arg(8, "pld");
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(128, 4) kron_matvec2d_kernel(MV2 a) {
                             dsum = fma(rr, rr, dsum);
                         } else if (EPI == POMS_EPI_AXPY) {
                             const double w_ = a.omega * v;
-                            a.y[idx] = a.b[idx] + w_;
+                            a.y[idx] = a.b ? a.b[idx] + w_ : w_;
                             dsum = fma(w_, w_, dsum);
                         } else {
                             double dg;
@@ -618,7 +618,7 @@ extern "C" int poms_kron_matvec_2d(const double* x, double* y, const double* b, 
                                    double* dot_out, void* ws, void* stream) {
     if (!x) return bad_arg(1, "x");
     if (!y) return bad_arg(2, "y");
-    if (epilogue != POMS_EPI_STORE && !b) return bad_arg(3, "b required by epilogue");
+    if (epilogue != POMS_EPI_STORE && epilogue != POMS_EPI_AXPY && !b) return bad_arg(3, "b required by epilogue");
     if (n1 < 1 || n2 < 1) return bad_arg(4, "extent");
     if (ld < n2) return bad_arg(6, "ld");
     if (glo < 0 || ghi < 0) return bad_arg(7, "ghost rows");
@@ -697,7 +697,7 @@ extern "C" int poms_stencil_matvec_2d(const double* x, double* y, const double* 
                                       int ghi, int p1, int p2, int epilogue, double omega,
                                       double* dot_out, void* ws, void* stream) {
     if (!x || !y || !S) return bad_arg(1, "null pointer");
-    if (epilogue != POMS_EPI_STORE && !b) return bad_arg(3, "b required by epilogue");
+    if (epilogue != POMS_EPI_STORE && epilogue != POMS_EPI_AXPY && !b) return bad_arg(3, "b required by epilogue");
     if (dot_out && !ws) return bad_arg(15, "ws");
     dim3 grid((n2 + 255) / 256, n1);
     if ((int64_t)grid.x * grid.y > POMS_MAX_PARTIALS) return bad_arg(5, "grid too large for ws");
@@ -1604,3 +1604,5 @@ extern "C" int poms_dense_matvec(const double* Ainv, const double* x, double* y,
     CHECK_LAUNCH("poms_dense_matvec");
     return 0;
 }
+
+#include "poms_transfer3d.cuh"

@@ -174,6 +174,7 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     // warps whose 32 columns x E rows lie outside the domain (ragged last tiles) skip stages 2 and 3
     const bool wlive = __ballot_sync(0xffffffffu, okmask != 0) != 0;
     constexpr bool NEED_B = (EPI != POMS_EPI_STORE);
+    const bool need_b = NEED_B && a.b != nullptr;   // AXPY without b: y = omega*v (zero initial guess)
     const bool need_x = (EPI == POMS_EPI_STORE && a.dot_out) || EPI == POMS_EPI_JACOBI;
     // output / rhs pointers of the NEXT plane to be emitted (planes are emitted in order)
     int64_t eoff = (int64_t)c_lo * a.pld + poff;
@@ -192,7 +193,7 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     if (okmask & (1u << e)) {
-                        if (NEED_B) cp_async8(pfb + pslot + e * T3, a.b + eoff + (int64_t)e * a.ld);
+                        if (need_b) cp_async8(pfb + pslot + e * T3, a.b + eoff + (int64_t)e * a.ld);
                         if (need_x) cp_async8(pfx + pslot + e * T3, a.x + eoff + (int64_t)e * a.ld);
                     }
                 }
@@ -365,7 +366,7 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                         dsum = fma(rr, rr, dsum);
                     } else if (EPI == POMS_EPI_AXPY) {
                         const double w_ = a.omega * v;
-                        yp[(int64_t)e * a.ld] = pfb[pslot + e * T3] + w_;
+                        yp[(int64_t)e * a.ld] = need_b ? pfb[pslot + e * T3] + w_ : w_;
                         dsum = fma(w_, w_, dsum);
                     } else {
                         const double dg = TWO ? dg1 * dA[e] + dg2 * dB[e] : dg1 * dA[e];
@@ -403,321 +404,6 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
     }
 }
 
-// =============================================================================================
-// Warp-private variant: every warp owns an 8-column strip of the tile (all rows) and runs the three
-// stages on it with __syncwarp only.  The TMA ring is shared by the CTA: full[] barriers carry the
-// transaction bytes, empty[] barriers collect one arrival per warp once its axis-3 pass has read the
-// slot; lane 0 of warp 0 is the producer.  No __syncthreads in the plane loop, so warps drift and
-// overlap each other's shared-memory and mbarrier latencies.
-// =============================================================================================
-template <int P>
-struct MV3WCfg {
-    static constexpr int W = 2 * P + 1;
-    static constexpr int T3 = 64, T2 = 16, E = 4, NW = 8, SW = 8;
-    static constexpr int SH = P & 1;
-    static constexpr int R2 = T2 + 2 * P;
-    static constexpr int NEED = T3 + 2 * P + 2 * SH;
-    static constexpr int C8 = ((NEED + 7) / 8) * 8;
-    static constexpr int C3 = (C8 % 16 == 8) ? C8 : C8 + 8;   // row pitch = 64 B mod 128 B
-    static constexpr int UP = 10;                              // pitch of the private su/sv rows
-    static constexpr int PD = 3, NST = PD + 1;
-    static constexpr int STAGE_BYTES = ((R2 * C3 * 8 + 127) / 128) * 128;
-    static constexpr int SUW = R2 * UP;                        // doubles per warp per array
-    static constexpr size_t smem_bytes(bool two) {
-        return (size_t)NST * STAGE_BYTES + (size_t)NW * (two ? 2 : 1) * SUW * 8 +
-               (size_t)2 * T2 * W * 8 + 16 * 8 + 32 * 8 + (size_t)2 * T2 * T3 * 8;
-    }
-};
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-
-template <int P, int FORM, int EPI>
-__global__ void __launch_bounds__(256, (P <= 3 ? POMS_MV3_MINB : 1))
-kron_matvec3d_wp_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MV3T g) {
-    using C = MV3WCfg<P>;
-    constexpr int W = C::W, T3 = C::T3, E = C::E, T2 = C::T2, R2 = C::R2, C3 = C::C3, NST = C::NST,
-                  SH = C::SH, PD = C::PD, UP = C::UP, NW = C::NW;
-    constexpr bool TWO = (FORM == POMS_FORM_SUM);
-    constexpr int NX = 2 * P + 2;
-    const MV3& a = g.a;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    double* const ring = reinterpret_cast<double*>(smem_raw);
-    double* const suv = ring + (size_t)NST * (C::STAGE_BYTES / 8);
-    double* const c2m = suv + (size_t)NW * (TWO ? 2 : 1) * C::SUW;
-    double* const c2k = c2m + T2 * W;
-    uint64_t* const full = reinterpret_cast<uint64_t*>(c2k + T2 * W);
-    uint64_t* const empty = full + 8;
-    double* const red = reinterpret_cast<double*>(full + 16);
-    double* const pfb = red + 32;
-    double* const pfx = pfb + T2 * T3;
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int ty = lane >> 3, cx = lane & 7, pr = lane & 3;
-    double* const su = suv + (size_t)wid * (TWO ? 2 : 1) * C::SUW;
-    double* const sv = su + C::SUW;
-    const int i3_0 = blockIdx.x * T3 - SH, i2_0 = blockIdx.y * T2;
-    const int c_lo = blockIdx.z * a.chunk;
-    const int c_hi = min(a.n1, c_lo + a.chunk);
-    const int tcol = 8 * wid + cx;
-    const int i3 = i3_0 + tcol;
-    const bool v3 = i3 >= 0 && i3 < a.n3;
-    const bool toep2 = (i2_0 >= g.lo2) && (i2_0 + T2 <= g.hi2);
-    const int ca = i3_0 + 8 * wid + 2 * pr, cb = ca + 1;
-    const bool toep3 = (ca >= g.lo3) && (cb < g.hi3);
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NST; ++s) {
-            mbar_init(full + s, 1);
-            mbar_init(empty + s, NW);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    }
-    if (!toep2) {
-        for (int t = tid; t < T2 * W; t += blockDim.x) {
-            const int r = t / W, k = t - r * W, i2 = i2_0 + r;
-            c2m[t] = i2 < a.n2 ? a.m2[(int64_t)i2 * W + k] : 0.0;
-            if (TWO) c2k[t] = i2 < a.n2 ? a.k2[(int64_t)i2 * W + k] : 0.0;
-        }
-    }
-    double dA[E], dB[E];
-    if (EPI == POMS_EPI_JACOBI || EPI == POMS_EPI_DINV) {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int i2 = i2_0 + ty * E + e;
-            const bool ok = v3 && i2 < a.n2;
-            const double m2d = ok ? a.m2[(int64_t)i2 * W + P] : 1.0;
-            const double m3d = ok ? a.m3[(int64_t)i3 * W + P] : 1.0;
-            dA[e] = m2d * m3d;
-            dB[e] = 0.0;
-            if (TWO) {
-                const double k2d = ok ? a.k2[(int64_t)i2 * W + P] : 0.0;
-                const double k3d = ok ? a.k3[(int64_t)i3 * W + P] : 0.0;
-                dB[e] = k2d * m3d + m2d * k3d;
-            }
-        }
-    }
-    double acc[E][W];
-#pragma unroll
-    for (int e = 0; e < E; ++e)
-#pragma unroll
-        for (int k = 0; k < W; ++k) acc[e][k] = 0.0;
-    double dsum = 0.0;
-
-    const int start = c_lo - P, end = c_hi + P;
-    auto valid = [&](int j1) { return j1 >= -a.glo && j1 < a.n1 + a.ghi; };
-    __syncthreads();
-    const bool producer = (tid == 0);
-    unsigned armed = 0, empty_bits = 0;   // producer-only state
-    if (producer) {
-#pragma unroll
-        for (int d = 0; d < PD; ++d) {
-            if (start + d < end && valid(start + d)) {
-                mbar_expect_tx(full + d, R2 * C3 * 8);
-                tma_load_3d(ring + (size_t)d * (C::STAGE_BYTES / 8), &tmap, i3_0 - P, i2_0 - P,
-                            start + d + a.glo, full + d);
-                armed |= 1u << d;
-            }
-        }
-    }
-    const int64_t poff = (int64_t)(i2_0 + ty * E) * a.ld + i3;
-    const int pslot = (ty * E) * T3 + tcol;
-    unsigned phase_bits = 0;
-    int u = 0, st = 0;
-#pragma unroll 1
-    for (int j1 = start; j1 < end; ++j1) {
-        const bool have = valid(j1);
-        const int i1 = j1 - P;
-        const bool emit = (i1 >= c_lo && i1 < c_hi);
-        constexpr bool NEED_B = (EPI != POMS_EPI_STORE);
-        const bool need_x = (EPI == POMS_EPI_STORE && a.dot_out) || EPI == POMS_EPI_JACOBI;
-        if (emit && v3) {
-            const int64_t o = (int64_t)i1 * a.pld + poff;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                if ((i2_0 + ty * E + e) < a.n2) {
-                    if (NEED_B) cp_async8(pfb + pslot + e * T3, a.b + o + (int64_t)e * a.ld);
-                    if (need_x) cp_async8(pfx + pslot + e * T3, a.x + o + (int64_t)e * a.ld);
-                }
-            }
-        }
-        cp_async_commit();
-        if (have) {
-            mbar_wait(full + st, (phase_bits >> st) & 1u);
-            phase_bits ^= (1u << st);
-            const double* const sx = ring + (size_t)st * (C::STAGE_BYTES / 8) + 8 * wid + 2 * pr;
-            // ---- stage 1: axis-3 pass on this warp's strip (88 = 22 rows x 4 column pairs) ----
-#pragma unroll 1
-            for (int rnd = 0; rnd < (4 * R2 + 31) / 32; ++rnd) {
-                const int row = (lane >> 2) + 8 * rnd;
-                if (row < R2) {
-                    double xr[NX];
-                    const double2* src = reinterpret_cast<const double2*>(sx + row * C3);
-#pragma unroll
-                    for (int q = 0; q < NX / 2; ++q) {
-                        const double2 v2 = src[q];
-                        xr[2 * q] = v2.x;
-                        xr[2 * q + 1] = v2.y;
-                    }
-                    double ua = 0.0, ub = 0.0, va = 0.0, vb = 0.0;
-                    if (toep3) {
-#pragma unroll
-                        for (int k = 0; k < W; ++k) {
-                            ua = fma(g.t3m[k], xr[k], ua);
-                            ub = fma(g.t3m[k], xr[k + 1], ub);
-                            if (TWO) {
-                                va = fma(g.t3k[k], xr[k], va);
-                                vb = fma(g.t3k[k], xr[k + 1], vb);
-                            }
-                        }
-                    } else {
-                        const bool oka = ca >= 0 && ca < a.n3, okb = cb >= 0 && cb < a.n3;
-#pragma unroll
-                        for (int k = 0; k < W; ++k) {
-                            const double ma = oka ? __ldg(a.m3 + (int64_t)ca * W + k) : 0.0;
-                            const double mb = okb ? __ldg(a.m3 + (int64_t)cb * W + k) : 0.0;
-                            ua = fma(ma, xr[k], ua);
-                            ub = fma(mb, xr[k + 1], ub);
-                            if (TWO) {
-                                const double ka = oka ? __ldg(a.k3 + (int64_t)ca * W + k) : 0.0;
-                                const double kb = okb ? __ldg(a.k3 + (int64_t)cb * W + k) : 0.0;
-                                va = fma(ka, xr[k], va);
-                                vb = fma(kb, xr[k + 1], vb);
-                            }
-                        }
-                    }
-                    *reinterpret_cast<double2*>(su + row * UP + 2 * pr) = make_double2(ua, ub);
-                    if (TWO) *reinterpret_cast<double2*>(sv + row * UP + 2 * pr) = make_double2(va, vb);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + st);   // this warp is done with ring slot st
-        }
-        // ---- producer: plane j1+PD goes into the slot that held plane j1-1 ----
-        if (producer && j1 + PD < end && valid(j1 + PD)) {
-            const int sn = (st + PD) % NST;
-            if (armed & (1u << sn)) {
-                mbar_wait(empty + sn, (empty_bits >> sn) & 1u);
-                empty_bits ^= (1u << sn);
-            }
-            mbar_expect_tx(full + sn, R2 * C3 * 8);
-            tma_load_3d(ring + (size_t)sn * (C::STAGE_BYTES / 8), &tmap, i3_0 - P, i2_0 - P,
-                        j1 + PD + a.glo, full + sn);
-            armed |= 1u << sn;
-        }
-        double ta[E], tb[E], vout[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) ta[e] = tb[e] = 0.0;
-        if (have) {
-            // ---- stage 2: axis-2 pass, scatter form ----
-            const double* const up = su + (ty * E) * UP + cx;
-            const double* const vp = sv + (ty * E) * UP + cx;
-            if (toep2) {
-#pragma unroll
-                for (int r = 0; r < E + 2 * P; ++r) {
-                    const double uv = up[r * UP];
-                    const double vv = TWO ? vp[r * UP] : 0.0;
-#pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        const int k = r - e;
-                        if (k >= 0 && k < W) {
-                            ta[e] = fma(g.t2m[k], uv, ta[e]);
-                            if (TWO) {
-                                tb[e] = fma(g.t2k[k], uv, tb[e]);
-                                tb[e] = fma(g.t2m[k], vv, tb[e]);
-                            }
-                        }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < E + 2 * P; ++r) {
-                    const double uv = up[r * UP];
-                    const double vv = TWO ? vp[r * UP] : 0.0;
-#pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        const int k = r - e;
-                        if (k >= 0 && k < W) {
-                            const double cm = c2m[(ty * E + e) * W + k];
-                            ta[e] = fma(cm, uv, ta[e]);
-                            if (TWO) {
-                                tb[e] = fma(c2k[(ty * E + e) * W + k], uv, tb[e]);
-                                tb[e] = fma(cm, vv, tb[e]);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();   // su/sv may be overwritten by the next plane's stage 1
-        // ---- stage 3: rotating axis-1 partial sums ----
-        const bool toep1 = have && (j1 - P >= g.lo1) && (j1 + P < g.hi1);
-        if (toep1) {
-            rot_scatter<W, E, TWO>(u, acc, ta, tb, *(const double(*)[W])(TWO ? g.t1k : g.t1m), *(const double(*)[W]) g.t1m, vout);
-        } else {
-            double c1k[W], c1m[W];
-#pragma unroll
-            for (int k = 0; k < W; ++k) {
-                const int o1 = j1 + P - k;
-                const bool ok = have && o1 >= 0 && o1 < a.n1;
-                if (TWO) {
-                    c1k[k] = ok ? __ldg(a.k1 + (int64_t)o1 * W + k) : 0.0;
-                    c1m[k] = ok ? __ldg(a.m1 + (int64_t)o1 * W + k) : 0.0;
-                } else {
-                    c1k[k] = ok ? __ldg(a.m1 + (int64_t)o1 * W + k) : 0.0;
-                    c1m[k] = 0.0;
-                }
-            }
-            rot_scatter<W, E, TWO>(u, acc, ta, tb, c1k, c1m, vout);
-        }
-        // ---- epilogue ----
-        cp_async_wait<0>();
-        if (emit) {
-            const int64_t o = (int64_t)i1 * a.pld + poff;
-            double dg1 = 0.0, dg2 = 0.0;
-            if (EPI == POMS_EPI_JACOBI || EPI == POMS_EPI_DINV) {
-                dg1 = TWO ? __ldg(a.k1 + (int64_t)i1 * W + P) : __ldg(a.m1 + (int64_t)i1 * W + P);
-                dg2 = TWO ? __ldg(a.m1 + (int64_t)i1 * W + P) : 0.0;
-            }
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                if (v3 && (i2_0 + ty * E + e) < a.n2) {
-                    const int64_t idx = o + (int64_t)e * a.ld;
-                    const double v = vout[e];
-                    if (EPI == POMS_EPI_STORE) {
-                        a.y[idx] = v;
-                        if (a.dot_out) dsum = fma(pfx[pslot + e * T3], v, dsum);
-                    } else if (EPI == POMS_EPI_RESID) {
-                        const double rr = pfb[pslot + e * T3] - v;
-                        a.y[idx] = rr;
-                        dsum = fma(rr, rr, dsum);
-                    } else if (EPI == POMS_EPI_AXPY) {
-                        const double w_ = a.omega * v;
-                        a.y[idx] = pfb[pslot + e * T3] + w_;
-                        dsum = fma(w_, w_, dsum);
-                    } else {
-                        const double dg = TWO ? dg1 * dA[e] + dg2 * dB[e] : dg1 * dA[e];
-                        const double dr = a.omega * (pfb[pslot + e * T3] - v) / dg;
-                        a.y[idx] = (EPI == POMS_EPI_JACOBI) ? pfx[pslot + e * T3] + dr : dr;
-                        dsum = fma(dr, dr, dsum);
-                    }
-                }
-            }
-        }
-        u = (u + 1 == W) ? 0 : u + 1;
-        st = (st + 1 == NST) ? 0 : st + 1;
-    }
-    if (a.dot_out) {
-        const double tot = block_sum(dsum, red);
-        const unsigned nb = gridDim.x * gridDim.y * gridDim.z;
-        const unsigned bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-        grid_sum_finish(tot, a.dot_out, a.ws, nb, bid, red);
-    }
-}
-
 // ---- host side -----------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -736,23 +422,8 @@ static PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
-static int g_mv3_variant = 0;   // 0: block-synchronous (default, measured faster), 1: warp-private strips
-extern "C" void poms_set_matvec3d_variant(int v) { g_mv3_variant = v; }
-
 template <int P, int FORM, int EPI>
 static int launch_mv3_tma_inst(const CUtensorMap& tm, const MV3T& g, dim3 grid, cudaStream_t st) {
-    if (g_mv3_variant == 1) {
-        const size_t smem = MV3WCfg<P>::smem_bytes(FORM == POMS_FORM_SUM);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(kron_matvec3d_wp_kernel<P, FORM, EPI>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(wp)");
-            attr_set = true;
-        }
-        kron_matvec3d_wp_kernel<P, FORM, EPI><<<grid, 256, smem, st>>>(tm, g);
-        return 0;
-    }
     const size_t smem = MV3TCfg<P>::smem_bytes(FORM == POMS_FORM_SUM);
     static bool attr_set = false;
     if (!attr_set) {
@@ -820,11 +491,7 @@ static int try_matvec3d_tma(const MV3& a0, int p, int form, int epilogue, const 
     CUtensorMap tm;
     cuuint64_t dims[3] = {(cuuint64_t)a0.n3, (cuuint64_t)a0.n2, (cuuint64_t)(a0.n1 + a0.glo + a0.ghi)};
     cuuint64_t strides[2] = {(cuuint64_t)a0.ld * 8, (cuuint64_t)a0.pld * 8};
-    int boxw = 64 + 2 * p + 2 * sh;
-    if (g_mv3_variant == 1) {   // MV3WCfg<P>::C3
-        const int c8 = ((boxw + 7) / 8) * 8;
-        boxw = (c8 % 16 == 8) ? c8 : c8 + 8;
-    }
+    const int boxw = 64 + 2 * p + 2 * sh;
     cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)(16 + 2 * p), 1};
     cuuint32_t es[3] = {1, 1, 1};
     void* gaddr = (void*)(a0.x - (int64_t)a0.glo * a0.pld);

@@ -16,9 +16,13 @@ Replaces the reference's MPI layer for the hot path
 Every method takes plain torch tensors whose first dimension is the plane index, so the
 communication logic runs unchanged on CPU tensors with the gloo backend (tests/test_dist_gloo.py).
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+from . import profiling
 
 
 def block_bounds(n, size, rank):
@@ -35,6 +39,14 @@ class Slab:
         self.rank = dist.get_rank(self.group)
         self.size = dist.get_world_size(self.group)
         self.device = device
+        # POMS_B200_OVERLAP=1: run the halo exchange of a 3-D mat-vec on a second stream while the
+        # ghost-free planes are computed.  OFF by default -- measured slower on 2 B200s (C5: 445 ms
+        # vs 337 ms): the mat-vec fills every SM's register file (2 x 256 threads x 128 registers), so
+        # NCCL's copy kernel only starts when a CTA retires, ~1/8 of the kernel later, which is longer
+        # than the 35 us exchange it was meant to hide.
+        self.overlap = (device is not None and torch.device(device).type == "cuda"
+                        and os.environ.get("POMS_B200_OVERLAP") == "1")
+        self._comm_stream = None
 
     # ---- partition ---------------------------------------------------------------------------
     def bounds(self, n, rank=None):
@@ -46,7 +58,8 @@ class Slab:
     # ---- collectives -------------------------------------------------------------------------
     def allreduce_sum(self, t):
         if self.size > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            with profiling.region("allreduce_scalar", 0):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
     def _peer(self, r):
@@ -69,13 +82,26 @@ class Slab:
                                   self._peer(hi_nb), self.group))
             ops.append(dist.P2POp(dist.irecv, buf[glo + n_own:glo + n_own + ghi],
                                   self._peer(hi_nb), self.group))
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+        with profiling.region("halo_exchange", 2 * 8 * width * buf[0].numel()):
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
 
     def exchange(self, v):
         """Halo exchange of a StencilVector (p planes per neighbour)."""
         V = v.space
         self.exchange_planes(v._buf, V.local_shape[0], V.glo, V.ghi, V.pads[0])
+
+    def exchange_async(self, v):
+        """The same exchange on the communication stream, ordered after the work already queued on
+        the current stream; returns the event the consumer of the ghost planes must wait for."""
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        cs = self._comm_stream
+        cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            self.exchange(v)
+            ev = cs.record_event()
+        return ev
 
     def gather_planes(self, own, table, need):
         """Planes need[0]..need[1] (global numbering, inclusive) of a plane-partitioned array of
@@ -113,8 +139,9 @@ class Slab:
                 ops.append(dist.P2POp(dist.isend, own[nlo - s:].contiguous(),
                                       self._peer(r + 1), self.group))
         if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+            with profiling.region("gather_planes", 0):
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
         return out
 
     def allgather_planes(self, own, table):

@@ -53,8 +53,13 @@ class _AxisOp:
     def __init__(self, start, coef, n_in, device):
         self.n_out, self.W = coef.shape
         self.n_in = int(n_in)
-        self.start = torch.as_tensor(np.ascontiguousarray(start, dtype=np.int32), device=device)
+        self._start_host = np.ascontiguousarray(start, dtype=np.int32)
+        self.start = torch.as_tensor(self._start_host, device=device)
         self.coef = torch.as_tensor(np.ascontiguousarray(coef, dtype=np.float64), device=device)
+
+    @property
+    def start_host(self):
+        return self._start_host
 
     def apply(self, src, dst, shape_in, ld_in, ld_out, axis, accumulate=False):
         """dst = op along `axis` of src.  src/dst are pitched arrays: logical shape `shape_in`
@@ -81,6 +86,36 @@ class _AxisOp:
 
 def _pitch(n):
     return n + (n & 1)
+
+
+def _fused_restrict(ops, fine, shape_f, ld_f, coarse, shape_c, ld_c):
+    """coarse = (R1 (x) R2 (x) R3) fine in one kernel; False if the rows do not fit its tiles."""
+    r1, r2, r3 = ops
+    rc = _lib.lib().poms_restrict_3d(
+        fine.data_ptr(), coarse.data_ptr(), shape_f[0], shape_f[1], shape_f[2], ld_f,
+        shape_f[1] * ld_f, shape_c[0], shape_c[1], shape_c[2], ld_c, shape_c[1] * ld_c,
+        r1.start.data_ptr(), r1.coef.data_ptr(), r1.W, r2.start.data_ptr(), r2.coef.data_ptr(), r2.W,
+        r3.start.data_ptr(), r3.coef.data_ptr(), r3.W, r1.start_host.ctypes.data,
+        r2.start_host.ctypes.data, r3.start_host.ctypes.data, _stream())
+    if rc < 0:
+        return False
+    _lib.check(rc, "poms_restrict_3d")
+    return True
+
+
+def _fused_prolong(ops, coarse, shape_c, ld_c, fine, shape_f, ld_f, accumulate):
+    """fine (+)= (P1 (x) P2 (x) P3) coarse in one kernel; False if the rows do not fit its tiles."""
+    p1, p2, p3 = ops
+    rc = _lib.lib().poms_prolong_3d(
+        coarse.data_ptr(), fine.data_ptr(), shape_f[0], shape_f[1], shape_f[2], ld_f,
+        shape_f[1] * ld_f, shape_c[0], shape_c[1], shape_c[2], ld_c, shape_c[1] * ld_c,
+        p1.start.data_ptr(), p1.coef.data_ptr(), p1.W, p2.start.data_ptr(), p2.coef.data_ptr(), p2.W,
+        p3.start.data_ptr(), p3.coef.data_ptr(), p3.W, p2.start_host.ctypes.data,
+        p3.start_host.ctypes.data, int(accumulate), _stream())
+    if rc < 0:
+        return False
+    _lib.check(rc, "poms_prolong_3d")
+    return True
 
 
 def _tmp(shape, ld, device, zero=True):
@@ -111,6 +146,15 @@ class Transfer:
             self.R.append(_AxisOp(stt, cft, nf, device))
             self.P1_rows.append((st, cf, nc))
         self.device = device
+        # 3-D with every axis refined: one fused kernel per transfer instead of three gathers, on the
+        # levels where launch latency dominates (measured at p = 3, tests/gpu_ab_transfer.py: fused
+        # 0.045 / 0.044 ms vs 0.085 / 0.073 ms at 131^3, but 0.77 / 1.41 ms vs 0.61 / 1.01 ms at 515^3,
+        # where the three streaming passes run closer to the HBM rate than the fused tile pipeline)
+        self.fused = self.ndim == 3 and all(op is not None for op in self.P)
+        self.fused_max = 6_000_000      # fine points per rank up to which the fused kernels are used
+
+    def _want_fused(self, shape_f):
+        return self.fused and int(np.prod(shape_f)) <= self.fused_max
 
     def restrict(self, rf, Vc):
         """r_c = (P1^T (x) .. (x) P1^T) r_f.  Axis 1 first: the largest array is read once,
@@ -119,6 +163,10 @@ class Transfer:
         rc = StencilVector(Vc)
         cur, ld = rf.flat, rf.ld
         shape = tuple(rf.space.local_shape)
+        if self._want_fused(shape):
+            if _fused_restrict(self.R, cur, shape, ld, rc.flat, tuple(Vc.local_shape), rc.ld):
+                return rc
+            self.fused = False
         ops = [(ax, op) for ax, op in enumerate(self.R) if op is not None]
         if not ops:
             rc.flat.copy_(cur)
@@ -141,6 +189,11 @@ class Transfer:
         pass along axis 1 accumulates straight into x_f (correction fused, mg_jac.py:112)."""
         cur, ld = ec.flat, ec.ld
         shape = tuple(ec.space.local_shape)
+        if self._want_fused(xf.space.local_shape):
+            if _fused_prolong(self.P, cur, shape, ld, xf.flat, tuple(xf.space.local_shape), xf.ld,
+                              True):
+                return xf
+            self.fused = False
         ops = [(ax, op) for ax, op in reversed(list(enumerate(self.P))) if op is not None]
         if not ops:
             xf.flat.add_(cur)
@@ -181,13 +234,42 @@ class DistTransfer(Transfer):
         self.R0 = _AxisOp(plan["R0"][r][0], plan["R0"][r][1], plan["R0"][r][2], device)
         self.P0 = _AxisOp(plan["P0"][r][0], plan["P0"][r][1], plan["P0"][r][2], device)
 
+    def _ghost_view(self, v, table, need):
+        """Planes need[rank] of `v` as a VIEW of its storage after a halo exchange (no copy), or
+        None when they reach beyond the ghost planes."""
+        V = v.space
+        s, e = table[self.slab.rank]
+        lo, hi = need[self.slab.rank]
+        # the same decision on every rank (the exchange is collective): table and need are global
+        if V.slab is None or any(ts - tl > V.pads[0] or th - te > V.pads[0]
+                                 for (ts, te), (tl, th) in zip(table, need)):
+            return None
+        assert s - lo <= V.glo and hi - e <= V.ghi
+        self.slab.exchange(v)
+        return v._buf[V.glo - (s - lo):V.glo + V.local_shape[0] + (hi - e)]
+
     def restrict(self, rf, Vc):
         slab = self.slab
         nd = len(rf.space.local_shape)
         ld = rf.ld
-        planes = slab.gather_planes(rf.flat, self.tf, self.need_f)
-        shape = (planes.shape[0],) + tuple(rf.space.local_shape[1:])
         cs, ce = self.tc[slab.rank]
+        # the neighbours' fine planes through the ghost planes (a view: no copy of the slab);
+        # gathered into a new array only when they reach beyond the ghosts
+        planes = self._ghost_view(rf, self.tf, self.need_f)
+        if planes is None:
+            planes = slab.gather_planes(rf.flat, self.tf, self.need_f)
+        shape_f = (planes.shape[0],) + tuple(rf.space.local_shape[1:])
+        if self._want_fused(shape_f):
+            rc = StencilVector(Vc)
+            shape_c = (ce - cs + 1,) + tuple(Vc.local_shape[1:])
+            dst = rc.flat if self.cdist else _tmp(shape_c, rc.ld, self.device)
+            if _fused_restrict((self.R0, self.R[1], self.R[2]), planes, shape_f, ld, dst, shape_c,
+                               rc.ld):
+                if not self.cdist:
+                    rc.flat.copy_(slab.allgather_planes(dst, self.tc))
+                return rc
+            self.fused = False
+        shape = (planes.shape[0],) + tuple(rf.space.local_shape[1:])
         ops = [(ax, op) for ax, op in enumerate(self.R) if op is not None and ax > 0]
         rc = StencilVector(Vc)
         own_view = rc.flat if self.cdist else None
@@ -220,6 +302,17 @@ class DistTransfer(Transfer):
         cur, ld = ec.flat, ec.ld
         shape = tuple(ec.space.local_shape)
         nd = len(shape)
+        # coarse planes of the neighbours through the ghost planes of e_c (a view), so that the
+        # in-plane passes below run on them too and no intermediate array has to be re-gathered
+        gview = self._ghost_view(ec, self.tc, self.need_c) if self.cdist else None
+        if gview is not None:
+            cur = gview
+            shape = (cur.shape[0],) + tuple(shape[1:])
+        if (gview is not None or not self.cdist) and self._want_fused(xf.space.local_shape):
+            if _fused_prolong((self.P0, self.P[1], self.P[2]), cur, shape, ld, xf.flat,
+                              tuple(xf.space.local_shape), xf.ld, True):
+                return xf
+            self.fused = False
         ops = [(ax, op) for ax, op in reversed(list(enumerate(self.P))) if op is not None and ax > 0]
         for ax, op in ops:
             shape_out = list(shape)
@@ -229,7 +322,7 @@ class DistTransfer(Transfer):
             shape = op.apply(cur, dst, shape, ld, ld_out, ax)
             cur, ld = dst, ld_out
         assert ld == xf.ld
-        if self.cdist:
+        if self.cdist and gview is None:
             planes = slab.gather_planes(cur, self.tc, self.need_c)
         else:
             planes = cur
@@ -375,11 +468,12 @@ class Hierarchy:
     """Dyadic hierarchy of nested spline spaces for -Lap u + u on [0,1]^d.
 
     N: elements per axis on the fine level (int or per-axis sequence); every level halves each
-    axis that still has more than `Nc` elements.  smoother: 'glt' | 'jacobi'.
+    axis that still has more than `Nc` elements (coarsen='semi') or all axes together until one
+    reaches `Nc` (coarsen='uniform').  smoother: 'glt' | 'glt_poly' | 'jacobi'.
     """
 
     def __init__(self, p, N, ndim=None, Nc=8, device="cuda", smoother="glt", nu=1, ratio=4.0,
-                 safety=1.1, slab=None, lengths=None, min_planes=32):
+                 safety=1.1, slab=None, lengths=None, min_planes=32, coarsen="semi"):
         if np.isscalar(N):
             N = [int(N)] * int(ndim)
         # domain [0, L_1] x .. x [0, L_d] (default the unit cube).  Weak scaling extends the domain
@@ -389,8 +483,22 @@ class Hierarchy:
         self.device = torch.device(device)
         self.smoother, self.nu, self.ratio, self.safety = smoother, nu, ratio, safety
         self.levels = []
-        Ns = list(N)
+        # grids of the hierarchy
+        grids = [list(N)]
         while True:
+            Ns = grids[-1]
+            if all(n <= Nc for n in Ns):
+                break
+            # coarsen='uniform': stop as soon as one axis cannot be halved, so the elements keep their
+            # shape on every level (elongated weak-scaling domains: semi-coarsening the long axis
+            # alone costs 5 of 22 iterations at 8 slabs); 'semi': keep halving the longer axes
+            if coarsen == "uniform" and not all(n > Nc and n % 2 == 0 for n in Ns):
+                break
+            nxt = [n // 2 if (n > Nc and n % 2 == 0) else n for n in Ns]
+            if nxt == Ns:
+                break
+            grids.append(nxt)
+        for i, Ns in enumerate(grids):
             lv = Level()
             lv.N = list(Ns)
             lv.knots = [bs.make_open_knots(p, n + p) * L for n, L in zip(Ns, self.lengths)]
@@ -398,8 +506,9 @@ class Hierarchy:
             # a level stays slab-partitioned while every slab keeps at least `min_planes` planes
             # (and enough for the p-wide halo and the 2q interface planes of the partitioned solve);
             # below that the per-operation latency of the exchanges exceeds the work, so the level is
-            # gathered and every rank works on the whole (small) grid redundantly
-            lv.distributed = (slab is not None and slab.size > 1
+            # gathered and every rank works on the whole (small) grid redundantly.  The coarsest
+            # level is always replicated: its exact solve is a replicated dense contraction.
+            lv.distributed = (slab is not None and slab.size > 1 and i < len(grids) - 1
                               and (not self.levels or self.levels[-1].distributed)
                               and (Ns[0] + p) >= slab.size * max(2 * p + 2, min_planes))
             # ghost planes along the slab axis: p for the operator, 2q for the F2 pass of glt_poly
@@ -408,20 +517,11 @@ class Hierarchy:
                                       [False] * self.ndim, device=self.device,
                                       slab=slab if lv.distributed else None)
             self.levels.append(lv)
-            if all(n <= Nc for n in Ns):
-                break
-            nxt = [n // 2 if (n > Nc and n % 2 == 0) else n for n in Ns]
-            if nxt == Ns:
-                break
-            Ns = nxt
         for f, c in zip(self.levels[:-1], self.levels[1:]):
             if f.distributed:
                 f.transfer = DistTransfer(c.knots, f.knots, p, self.device, slab, c.distributed)
             else:
                 f.transfer = Transfer(c.knots, f.knots, p, self.device)
-        if slab is not None and slab.size > 1 and self.levels[-1].distributed:
-            raise NotImplementedError("the coarsest level must be replicated: use a larger Nc "
-                                      "or fewer ranks")
         self.coarse = CoarseSolver(self.levels[-1].A, self.device)
         for lv in self.levels[:-1]:
             self._setup_smoother(lv)
@@ -506,8 +606,10 @@ class Hierarchy:
                     src = r
                 lv.S1.apply(src, t1, EPI_STORE)
                 # in place: the epilogue reads x[i] and writes x[i] from the same thread, and the
-                # mat-vec input is t1, so no other thread reads x
-                lv.S2.apply(t1, x, EPI_AXPY, b=x, omega=1.0 / theta)
+                # mat-vec input is t1, so no other thread reads x.  Zero guess: x = (1/theta) S2 t1,
+                # x is neither cleared nor read (b = None).
+                lv.S2.apply(t1, x, EPI_AXPY, b=None if (k == 0 and zero_guess) else x,
+                            omega=1.0 / theta)
             return x
         if self.smoother == "glt" and self.nu == 1 and all(lu.nopiv for lu in lv.glt_lu):
             # one step: x <- x + (1/theta) B^-1 (b - A x); the update is fused into the last line
@@ -553,7 +655,8 @@ def vcycle(h, l, b):
     lv = h.levels[l]
     if l == len(h.levels) - 1:
         return h.coarse.solve(b)
-    x = StencilVector(lv.V)
+    # the polynomial smoother overwrites x on a zero guess; the others accumulate into it
+    x = StencilVector(lv.V, zero=(h.smoother != "glt_poly"))
     h.smooth(lv, b, x, True)
     r = StencilVector(lv.V, zero=False)
     lv.A.apply(x, r, EPI_RESID, b=b)

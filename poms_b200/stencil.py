@@ -541,35 +541,65 @@ class KronSumMatrix:
         """y = epilogue(A x) in one fused pass; optional fused reduction into *dot_ptr."""
         V = x.space
         assert V.npts == self.npts, (V.npts, self.npts)
-        if V.slab is not None:
-            V.slab.exchange(x)
         ctx = DeviceContext.get(V.device)
         m, k = self._bands(V)
         kp = [t.data_ptr() if t is not None else None for t in k]
         L = _lib.lib()
         bp = b.ptr if b is not None else None
         # algorithmic bytes: read x, write y (+ read b for the fused residual/Jacobi epilogues)
-        nbytes = (16 if epi == EPI_STORE else 24) * V.local_size
+        nbytes = (16 if (epi == EPI_STORE or bp is None) else 24) * V.local_size
+        slab = V.slab
+        n1 = V.local_shape[0]
+        P = self.P
+        if (slab is not None and slab.size > 1 and self.ndim == 3 and dot_ptr is None
+                and n1 >= 4 * P and slab.overlap):
+            # Slab-partitioned 3-D pass without a fused reduction: the halo exchange runs on the
+            # communication stream WHILE the planes that need no ghost data are computed; the P
+            # planes next to each neighbour follow once the ghosts have arrived.
+            lo = P if slab.rank > 0 else 0
+            hi = P if slab.rank < slab.size - 1 else 0
+            ev = slab.exchange_async(x)
+            inner = nbytes * (n1 - lo - hi) // n1
+            with profiling.region("kron_matvec_3d", inner):
+                self._launch(L, V, x, y, bp, m, kp, epi, omega, None, ctx, lo, n1 - hi)
+            torch.cuda.current_stream().wait_event(ev)
+            with profiling.region("kron_matvec_3d_edge", nbytes - inner, launches=(lo > 0) + (hi > 0)):
+                if lo:
+                    self._launch(L, V, x, y, bp, m, kp, epi, omega, None, ctx, 0, lo)
+                if hi:
+                    self._launch(L, V, x, y, bp, m, kp, epi, omega, None, ctx, n1 - hi, n1)
+            return
+        if slab is not None:
+            slab.exchange(x)
         with profiling.region("kron_matvec_%dd" % self.ndim, nbytes):
             self._launch(L, V, x, y, bp, m, kp, epi, omega, dot_ptr, ctx)
 
-    def _launch(self, L, V, x, y, bp, m, kp, epi, omega, dot_ptr, ctx):
+    def _launch(self, L, V, x, y, bp, m, kp, epi, omega, dot_ptr, ctx, z0=0, z1=None):
+        """One kernel launch for the output planes [z0, z1) of the slab (default: all of them).  A
+        sub-range is the same kernel on shifted pointers: the planes outside it are ghost planes of
+        the sub-problem (glo + z0 below, ghi + n1 - z1 above)."""
         if self.ndim == 2:
             n1, n2 = V.local_shape
+            assert z0 == 0 and z1 is None
             _lib.check(L.poms_kron_matvec_2d(
                 x.ptr, y.ptr, bp, n1, n2, x.ld, V.glo, V.ghi, self.P, self.form,
                 m[0].data_ptr(), kp[0], m[1].data_ptr(), kp[1], epi, float(omega), dot_ptr,
                 ctx.ws_ptr, _stream()), "poms_kron_matvec_2d")
         else:
             n1, n2, n3 = V.local_shape
+            z1 = n1 if z1 is None else z1
             coef, rng = self._toeplitz()
             rng = rng.copy()
             # axis-1 rows are the slab's: shift the global interior range to local row numbers
-            rng[0] = max(0, int(rng[0]) - V.starts[0])
-            rng[1] = min(n1, int(rng[1]) - V.starts[0])
+            rng[0] = max(0, int(rng[0]) - V.starts[0] - z0)
+            rng[1] = max(int(rng[0]), min(z1 - z0, int(rng[1]) - V.starts[0] - z0))
+            W = 2 * self.P + 1
+            off = 8 * z0 * x.pld                        # bytes from plane 0 to plane z0
             _lib.check(L.poms_kron_matvec_3d_ex(
-                x.ptr, y.ptr, bp, n1, n2, n3, x.ld, x.pld, V.glo, V.ghi, self.P, self.form,
-                m[0].data_ptr(), kp[0], m[1].data_ptr(), kp[1], m[2].data_ptr(), kp[2], epi,
+                x.ptr + off, y.ptr + off, bp + off if bp is not None else None, z1 - z0, n2, n3,
+                x.ld, x.pld, V.glo + z0, V.ghi + n1 - z1, self.P, self.form,
+                m[0].data_ptr() + 8 * z0 * W, kp[0] + 8 * z0 * W if kp[0] is not None else None,
+                m[1].data_ptr(), kp[1], m[2].data_ptr(), kp[2], epi,
                 float(omega), dot_ptr, ctx.ws_ptr, _stream(), coef.ctypes.data, rng.ctypes.data),
                 "poms_kron_matvec_3d_ex")
 

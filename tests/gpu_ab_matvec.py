@@ -23,9 +23,8 @@ L = _lib.lib()
 dof = V.local_size
 for epi, name, nb in ((EPI_STORE, "store+dot", 16), (EPI_RESID, "resid", 24), (EPI_JACOBI, "jacobi", 24)):
     res = {}
-    for force in (1, 0, 2):
+    for force in (1, 2):
         L.poms_set_force_generic(1 if force == 1 else 0)
-        L.poms_set_matvec3d_variant(0 if force == 2 else 1)
         out = y if force == 1 else y2
         for _ in range(3):
             A.apply(x, out, epi, b=b, omega=0.5, dot_ptr=ctx.sptr(20 + force))
@@ -42,6 +41,5 @@ for epi, name, nb in ((EPI_STORE, "store+dot", 16), (EPI_RESID, "resid", 24), (E
         print("%-10s %-8s %8.3f ms  %7.1f GB/s (alg %d B/DOF)  dot=%.15e" % (
             name, {1: "generic", 0: "tma-wp", 2: "tma-blk"}[force], ms, nb * dof / ms / 1e6, nb, ctx.scal[20 + force].item()))
     diff = (y.data - y2.data).abs().max().item() / y.data.abs().max().item()
-    print("   max rel diff generic vs tma: %.2e   speedup wp %.2fx  blk %.2fx" % (diff, res[1] / res[0], res[1] / res[2]))
+    print("   max rel diff generic vs tma: %.2e   speedup %.2fx" % (diff, res[1] / res[2]))
 L.poms_set_force_generic(0)
-L.poms_set_matvec3d_variant(0)

@@ -1,0 +1,46 @@
+"""A/B timing of the grid transfers: fused one-pass kernels vs per-axis gathers -- run on the GPU box:
+    python tests/gpu_ab_transfer.py [N] [p]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from poms_b200 import bsplines as bs
+from poms_b200.mg import Transfer
+from poms_b200.stencil import StencilVectorSpace, StencilVector
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+p = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev).manual_seed(0)
+while N >= 64:
+    Tf = [bs.make_open_knots(p, N + p)] * 3
+    Tc = [bs.make_open_knots(p, N // 2 + p)] * 3
+    Vf = StencilVectorSpace([N + p] * 3, [p] * 3, [False] * 3, device=dev)
+    Vc = StencilVectorSpace([N // 2 + p] * 3, [p] * 3, [False] * 3, device=dev)
+    tr = Transfer(Tc, Tf, p, dev)
+    rf, xf, ec = StencilVector(Vf), StencilVector(Vf), StencilVector(Vc)
+    rf.data.copy_(torch.randn(Vf.npts, generator=g, dtype=torch.float64, device=dev))
+    ec.data.copy_(torch.randn(Vc.npts, generator=g, dtype=torch.float64, device=dev))
+    res = {}
+    for fused in (False, True):
+        tr.fused, tr.fused_max = fused, 10 ** 12
+        xf.flat.zero_()
+        rc = tr.restrict(rf, Vc)
+        tr.prolong_add(ec, xf)
+        res[fused] = (rc.data.clone(), xf.data.clone())
+        for name, fn in (("restrict", lambda: tr.restrict(rf, Vc)), ("prolong_add", lambda: tr.prolong_add(ec, xf))):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            print("n=%4d %-12s %-8s %8.4f ms" % (N + p, name, "fused" if fused else "per-axis", e0.elapsed_time(e1) / reps), flush=True)
+        assert tr.fused == fused
+    dr = (res[True][0] - res[False][0]).abs().max().item() / res[False][0].abs().max().item()
+    dp = (res[True][1] - res[False][1]).abs().max().item() / res[False][1].abs().max().item()
+    print("   max rel diff fused vs per-axis: restrict %.1e prolong %.1e" % (dr, dp))
+    N //= 2

@@ -71,15 +71,16 @@ for (p, N) in ((3, (32 * world, 16, 24)), (2, (64, 40)), (3, (64 * world, 32)), 
           info["niter"] == io["niter"] and err < 1e-8 and np.allclose(info["history"], io["history"], rtol=1e-5),
           "iters %d vs %d, err %.1e" % (info["niter"], io["niter"], err))
     # polynomial GLT smoother: wider (2q) halo along the slab axis, no SPIKE on the smoother path
-    h = Hierarchy(p, list(N), device=dev, slab=slab, lengths=lengths, min_planes=8, smoother="glt_poly")
-    ho = po.MGHierarchy(p, list(N), lengths=lengths, smoother="glt_poly")
+    h = Hierarchy(p, list(N), device=dev, slab=slab, lengths=lengths, min_planes=8, smoother="glt_poly",
+                  coarsen="uniform")
+    ho = po.MGHierarchy(p, list(N), lengths=lengths, smoother="glt_poly", coarsen="uniform")
     bb = StencilVector(h.levels[0].V)
     bb.data.fill_(1.0)
     xs, info = mg_pcg(h, bb, tol=1e-10, maxiter=100)
     xo, io = ho.mg_pcg(np.ones(npts), tol=1e-10, maxiter=100)
     s2, e2 = h.levels[0].V.starts[0], h.levels[0].V.ends[0]
     err = np.abs(xs.data.cpu().numpy() - xo[s2:e2 + 1]).max() / np.abs(xo).max()
-    check("mg_pcg glt_poly %dD p=%d N=%s" % (d, p, N),
+    check("mg_pcg glt_poly uniform-coarsening %dD p=%d N=%s levels=%d" % (d, p, N, len(h.levels)),
           info["niter"] == io["niter"] and err < 1e-8, "iters %d vs %d, err %.1e" % (info["niter"], io["niter"], err))
 if rank == 0:
     print("ALL OK" if ok else "SOME FAILED")

@@ -381,7 +381,8 @@ def test_two_grid_golden(dev, golden, name):
     assert np.abs(_arr(out["x_c"]).ravel() - g["x_c"]).max() < 1e-9 * amp * xs
 
 
-@pytest.mark.parametrize("p,N", [(3, (16, 16)), (2, (8, 16)), (3, (8, 8, 8)), (1, (4, 8, 16))])
+@pytest.mark.parametrize("p,N", [(3, (16, 16)), (2, (8, 16)), (3, (8, 8, 8)), (1, (4, 8, 16)),
+                                 (3, (20, 36, 140)), (5, (12, 44, 72)), (2, (66, 18, 130)), (4, (6, 6, 6))])
 def test_transfer_and_coarse_solver_vs_oracle(dev, p, N):
     from poms_b200 import bsplines as bs
     from poms_b200.stencil import KronSumMatrix
@@ -400,10 +401,18 @@ def test_transfer_and_coarse_solver_vs_oracle(dev, p, N):
         P1s.append(po.insertion_matrix(ts, Nc[a] + p, p, Tc[a]))
     rng = np.random.default_rng(11)
     rf, ec, xf = rng.standard_normal(Vf.npts), rng.standard_normal(Vc.npts), rng.standard_normal(Vf.npts)
-    assert rel(_arr(tr.restrict(_vec(Vf, rf), Vc)), po.restrict(P1s, rf)) < 1e-13
-    x = _vec(Vf, xf)
-    tr.prolong_add(_vec(Vc, ec), x)
-    assert rel(_arr(x), xf + po.prolong(P1s, ec)) < 1e-13
+    # 3-D: the fused one-pass kernels (poms_restrict_3d / poms_prolong_3d), then the per-axis gathers
+    for fused in ([True, False] if d == 3 else [False]):
+        assert tr.fused == (d == 3)
+        tr.fused, tr.fused_max = fused, 10 ** 12
+        assert rel(_arr(tr.restrict(_vec(Vf, rf), Vc)), po.restrict(P1s, rf)) < 1e-13
+        x = _vec(Vf, xf)
+        tr.prolong_add(_vec(Vc, ec), x)
+        assert rel(_arr(x), xf + po.prolong(P1s, ec)) < 1e-13
+        assert tr.fused == fused            # no silent fall-back to the gathers
+        tr.fused = d == 3
+    if max(N) > 64:
+        return
     Ac = KronSumMatrix.poisson(p, Tc)
     Aco, _, _ = po.poisson_operator(p, Tc)
     bc = rng.standard_normal(Vc.npts)
