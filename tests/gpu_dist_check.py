@@ -1,5 +1,5 @@
 """Multi-GPU parity check (run under torchrun on the GPU box):
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/gpu_dist_check.py
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/gpu_dist_check.py
 Compares the slab-partitioned path (halo exchange, SPIKE solve, distributed transfers, gathered coarse
 levels) with the CPU oracle on the same global problem: identical MG-PCG iteration counts."""
 import os, sys
@@ -70,7 +70,21 @@ for (p, N) in ((3, (32 * world, 16, 24)), (2, (64, 40)), (3, (64 * world, 32)), 
     check("mg_pcg %dD p=%d N=%s levels dist=%s" % (d, p, N, [int(l.distributed) for l in h.levels]),
           info["niter"] == io["niter"] and err < 1e-8 and np.allclose(info["history"], io["history"], rtol=1e-5),
           "iters %d vs %d, err %.1e" % (info["niter"], io["niter"], err))
-    # polynomial GLT smoother: wider (2q) halo along the slab axis, no SPIKE on the smoother path
+    # polynomial GLT smoother: wider (2q) halo along the slab axis, no SPIKE on the smoother path.
+    # Uniform coarsening stops early on elongated grids and the ORACLE inverts its coarsest operator
+    # densely: keep that grid below ~5000 unknowns (a 31 000-unknown inverse once took this script
+    # past a 15-minute limit on 4 GPUs).
+    Nu = list(N)
+    while True:
+        g = list(Nu)
+        while all(n > 8 and n % 2 == 0 for n in g):
+            g = [n // 2 for n in g]
+        if np.prod([n + p for n in g]) <= 5000 or Nu[0] <= 16 * world:
+            break
+        Nu[0] //= 2
+    N = tuple(Nu)
+    npts = [n + p for n in N]
+    lengths = [n / min(N) for n in N]
     h = Hierarchy(p, list(N), device=dev, slab=slab, lengths=lengths, min_planes=8, smoother="glt_poly",
                   coarsen="uniform")
     ho = po.MGHierarchy(p, list(N), lengths=lengths, smoother="glt_poly", coarsen="uniform")

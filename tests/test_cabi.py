@@ -48,6 +48,31 @@ def test_argument_validation_happens_before_cuda():
         _lib.check(rc, "poms_band_solve_axis")
 
 
+def test_fused_transfer_checks_rows_against_its_tiles_on_the_host():
+    """poms_restrict_3d / poms_prolong_3d refuse rows that do not fit their static tiles (the caller
+    then uses poms_axis_gather) -- decided from the host copies of the starts, before any launch."""
+    import numpy as np
+    from poms_b200 import bsplines as bs
+    L = _lib.lib()
+    p, Nc = 3, 16
+    st, cf, _ = bs.knot_insertion_rows(bs.make_open_knots(p, Nc + p), bs.make_open_knots(p, 2 * Nc + p), p)
+    stt, cft = bs.rows_transpose(st, cf, Nc + p)
+    s_ok = np.ascontiguousarray(stt, dtype=np.int32)
+    nf, nc = 2 * Nc + p, Nc + p
+    args = lambda s1, s2, s3, W: (1, 1, nf, nf, nf, nf + 1, nf * (nf + 1), nc, nc, nc, nc + 1, nc * (nc + 1),
+                                  1, 1, W, 1, 1, W, 1, 1, W, s1.ctypes.data, s2.ctypes.data,
+                                  s3.ctypes.data, None)
+    # rows as wide as the kernel allows at most 8 taps
+    assert L.poms_restrict_3d(*args(s_ok, s_ok, s_ok, 9)) == -15
+    # starts that jump by 8 per coarse row: a tile of 8 rows would need 61 fine rows (> 22)
+    s_bad = np.ascontiguousarray(np.arange(nc) * 8, dtype=np.int32)
+    assert L.poms_restrict_3d(*args(s_ok, s_bad, s_ok, cft.shape[1])) == -22
+    assert b"poms_axis_gather" in L.poms_last_error()
+    # decreasing starts along axis 1
+    assert L.poms_restrict_3d(*args(np.ascontiguousarray(s_ok[::-1]), s_ok, s_ok, cft.shape[1])) == -22
+    assert L.poms_restrict_3d(None, *args(s_ok, s_ok, s_ok, 5)[1:]) == -1
+
+
 def test_no_cpu_path():
     import torch
     from poms_b200.stencil import DeviceContext

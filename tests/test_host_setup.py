@@ -95,3 +95,18 @@ def test_kron_sum_host_form_equals_reference_assembly(golden, tag):
     assert rel(A.diagonal_host(), g["A"][:, :, p, p]) < 1e-13
     assert abs(A[3, 4, 0, 0] - g["A"][3, 4, p, p]) < 1e-15
     assert abs(A[3, 4, 1, -1] - g["A"][3, 4, p + 1, p - 1]) < 1e-15
+
+
+def test_oracle_uniform_coarsening_keeps_the_element_shape():
+    """coarsen='uniform' stops when one axis cannot be halved; 'semi' keeps halving the others
+    (the weak-scaling bench uses 'uniform')."""
+    from oracle import poms_oracle as po
+    hu = po.MGHierarchy(2, [32, 8, 8], Nc=4, coarsen="uniform")
+    hs = po.MGHierarchy(2, [32, 8, 8], Nc=4, coarsen="semi")
+    assert [lv["N"] for lv in hu.levels] == [[32, 8, 8], [16, 4, 4]]
+    assert [lv["N"] for lv in hs.levels] == [[32, 8, 8], [16, 4, 4], [8, 4, 4], [4, 4, 4]]
+    b = np.ones([n + 2 for n in (32, 8, 8)])
+    xu, iu = hu.mg_pcg(b, tol=1e-10, maxiter=60)
+    xs, is_ = hs.mg_pcg(b, tol=1e-10, maxiter=60)
+    assert iu["success"] and is_["success"] and iu["niter"] <= is_["niter"]
+    assert np.abs(xu - xs).max() < 1e-8 * np.abs(xs).max()
