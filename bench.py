@@ -96,7 +96,7 @@ class ClockSampler:
 _cpu_port = {}
 
 
-def cpu_port_solve(ndim, p, N, tol=1e-10):
+def cpu_port_solve(ndim, p, N, tol=1e-10, smoother="glt"):
     """One MG-PCG solve with the CPU port of the same algorithm: oracle/poms_oracle_mt.py (numba,
     all host threads), or the single-threaded NumPy oracle if numba is unavailable.  b = A x0 like
     the GPU arm.  Returns (dof, seconds, info, cores, label)."""
@@ -112,7 +112,7 @@ def cpu_port_solve(ndim, p, N, tol=1e-10):
             from oracle import poms_oracle as po
             _cpu_port.update(mod=po, cls=po.MGHierarchy, cores=1,
                              label="NumPy/SciPy oracle, single thread (numba unavailable: %s)" % exc)
-    h = _cpu_port["cls"](p, [N] * ndim, smoother="glt", nu=1)
+    h = _cpu_port["cls"](p, [N] * ndim, smoother=smoother, nu=1)
     A = h.levels[0]["A"]
     x0 = np.zeros(A.npts)
     for a in range(ndim):
@@ -124,6 +124,15 @@ def cpu_port_solve(ndim, p, N, tol=1e-10):
     x, info = h.mg_pcg(b, tol=tol, maxiter=200)
     dt = time.perf_counter() - t0
     return int(np.prod(b.shape)), dt, info, _cpu_port["cores"], _cpu_port["label"]
+
+
+def resolve_smoother(name, p):
+    """'auto': the polynomial GLT smoother (three fused Kronecker band passes) where its second
+    factor fits the kernels' half-bandwidth limit (2 <= p <= 3); exact GLT line solves otherwise.
+    Both arms (GPU and CPU port) use the same choice."""
+    if name == "auto":
+        return "glt_poly" if 2 <= p <= 3 else "glt"
+    return name
 
 
 def cpu_sample_size(ndim):
@@ -158,7 +167,8 @@ def run_reference(args, rank):
     vals = []
     t_all = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        dof, dt, info, cores, label = cpu_port_solve(ndim, p, Ns)
+        dof, dt, info, cores, label = cpu_port_solve(ndim, p, Ns,
+                                                     smoother=resolve_smoother(args.smoother, p))
         if i >= args.warmup:
             vals.append(dof / dt)
         if time.perf_counter() - t_all > 200 and vals:
@@ -173,8 +183,8 @@ def run_reference(args, rank):
                                % (desc, Ns, ndim), "p": p, "ndim": ndim, "elements_per_axis": Ns,
                    "iterations": info["niter"]},
         "cpu_baseline": {"value": v, "unit": "DOF/s", "cores": cores, "kind": "port",
-                         "sample": "%d^%d elements, %s, full MG-PCG solve to 1e-10"
-                                   % (Ns, ndim, label)},
+                         "sample": "%d^%d elements, %s, %s smoother, full MG-PCG solve to 1e-10"
+                                   % (Ns, ndim, label, resolve_smoother(args.smoother, p))},
         "e2e": {"value": v, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     _emit(line)
@@ -221,10 +231,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         slab = Slab(dist.group.WORLD, dev)
     ndim, p, N, desc = CONFIGS[args.config]
-    if args.smoother == "auto":
-        # polynomial GLT smoother (three fused Kronecker band passes) where its second factor fits
-        # the kernels' half-bandwidth limit (p <= 3); exact GLT line solves otherwise
-        args.smoother = "glt_poly" if 2 <= p <= 3 else "glt"
+    args.smoother = resolve_smoother(args.smoother, p)
     Ns = [N] * ndim
     if world > 1:
         Ns[0] = N * world          # weak scaling: N element planes per GPU along axis 1
@@ -390,13 +397,15 @@ def main():
         line["kron_matvec"] = {"achieved_gbs": k["gbs"], "frac_of_peak": k["gbs"] / peak,
                                "launches": k["launches"]}
     if not args.no_cpu_baseline:
-        Nc = min(N, cpu_sample_size(ndim))
-        dofc, dtc, infoc, cores, label = cpu_port_solve(ndim, p, Nc)
+        Ns_cpu = min(N, cpu_sample_size(ndim))
+        # the CPU port has the two GLT smoothers only
+        smo = "glt" if args.smoother == "jacobi" else args.smoother
+        dofc, dtc, infoc, cores, label = cpu_port_solve(ndim, p, Ns_cpu, smoother=smo)
         line["cpu_baseline"] = {"value": dofc / dtc, "unit": "DOF/s", "cores": cores, "kind": "port",
                                 "host_cores_available": os.cpu_count(),
                                 "sample": "%d^%d elements (%d DOF), one full MG-PCG solve to 1e-10, "
-                                          "%s, %d iterations, %.1f s"
-                                          % (Nc, ndim, dofc, label, infoc["niter"], dtc)}
+                                          "%s, %s smoother, %d iterations, %.1f s"
+                                          % (Ns_cpu, ndim, dofc, label, smo, infoc["niter"], dtc)}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -188,6 +188,17 @@ class MGHierarchyMT(po.MGHierarchy):
     def smooth(self, lv, b, x, zero_guess):
         A = lv["A"]
         theta = 0.5 * (lv["lmax"] + lv["lmin"])
+        if self.smoother == "glt_poly":          # poms_oracle.MGHierarchy.smooth, threaded band passes
+            for k in range(self.nu):
+                z = b if (k == 0 and zero_guess) else b - A.dot(x)
+                for ax in range(A.ndim):
+                    c = lv["qc"][ax]
+                    y = c[-1] * z
+                    for cf in c[-2::-1]:
+                        y = apply_band(lv["gband"][ax], y, ax) + cf * z
+                    z = y
+                x = x + z / theta
+            return x
         delta = 0.5 * (lv["lmax"] - lv["lmin"])
         sigma = theta / delta
         rho = 1.0 / sigma
