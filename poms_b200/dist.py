@@ -165,6 +165,19 @@ class Slab:
         return full
 
 
+def ghost_view_range(table, need, rank, width, glo, n_own):
+    """Planes need[rank] = [lo, hi] of a slab-partitioned array as a slice [a, b) of the rank's
+    storage [glo ghost planes | n_own owned | ghost planes] once a halo exchange of `width` planes
+    has filled the ghosts -- or None when SOME rank needs more than `width` planes of a neighbour
+    (the decision must be the same on every rank: the exchange is collective)."""
+    if any(ts - tl > width or th - te > width for (ts, te), (tl, th) in zip(table, need)):
+        return None
+    s, e = table[rank]
+    lo, hi = need[rank]
+    assert s - lo <= glo
+    return glo - (s - lo), glo + n_own + (hi - e)
+
+
 # ==========================================================================================
 # plan of the axis-1 grid transfer between two slab-partitioned (or partitioned -> replicated) levels
 # ==========================================================================================

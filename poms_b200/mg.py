@@ -237,16 +237,15 @@ class DistTransfer(Transfer):
     def _ghost_view(self, v, table, need):
         """Planes need[rank] of `v` as a VIEW of its storage after a halo exchange (no copy), or
         None when they reach beyond the ghost planes."""
+        from .dist import ghost_view_range
         V = v.space
-        s, e = table[self.slab.rank]
-        lo, hi = need[self.slab.rank]
-        # the same decision on every rank (the exchange is collective): table and need are global
-        if V.slab is None or any(ts - tl > V.pads[0] or th - te > V.pads[0]
-                                 for (ts, te), (tl, th) in zip(table, need)):
+        if V.slab is None:
             return None
-        assert s - lo <= V.glo and hi - e <= V.ghi
+        rng = ghost_view_range(table, need, self.slab.rank, V.pads[0], V.glo, V.local_shape[0])
+        if rng is None:
+            return None
         self.slab.exchange(v)
-        return v._buf[V.glo - (s - lo):V.glo + V.local_shape[0] + (hi - e)]
+        return v._buf[rng[0]:rng[1]]
 
     def restrict(self, rf, Vc):
         slab = self.slab

@@ -12,7 +12,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from poms_b200 import bsplines as bs
-from poms_b200.dist import (Slab, block_bounds, SpikeSetup, spike_solve_host, slab_transfer_plan)
+from poms_b200.dist import (Slab, block_bounds, SpikeSetup, spike_solve_host, slab_transfer_plan,
+                             ghost_view_range)
 
 
 def _free_port():
@@ -69,6 +70,20 @@ def _worker(rank, world, port, p, N, coarse_distributed):
         planes = slab.gather_planes(own_f, tf, plan["need_f"]).numpy()
         lo, hi = plan["need_f"][rank]
         assert np.array_equal(planes, Xg[lo:hi + 1])
+        # the same planes as a VIEW of the halo-exchanged storage (what DistTransfer uses when the
+        # neighbours' planes lie within the ghost width; no copy of the slab)
+        for width in (p, p + 1, 1):
+            g_lo = width if rank > 0 else 0
+            g_hi = width if rank < world - 1 else 0
+            rngv = ghost_view_range(tf, plan["need_f"], rank, width, g_lo, e - s + 1)
+            fits = all(ts - tl <= width and th - te <= width
+                       for (ts, te), (tl, th) in zip(tf, plan["need_f"]))
+            assert (rngv is not None) == fits
+            if rngv is not None:
+                gb = torch.zeros((g_lo + e - s + 1 + g_hi, m), dtype=torch.float64)
+                gb[g_lo:g_lo + e - s + 1] = own_f
+                slab.exchange_planes(gb, e - s + 1, g_lo, g_hi, width)
+                assert np.array_equal(gb[rngv[0]:rngv[1]].numpy(), planes)
         r0s, r0c, r0n = plan["R0"][rank]
         assert r0n == hi - lo + 1
         rc_own = _rows_apply(r0s, r0c, planes)
