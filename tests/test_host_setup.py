@@ -110,3 +110,78 @@ def test_oracle_uniform_coarsening_keeps_the_element_shape():
     xs, is_ = hs.mg_pcg(b, tol=1e-10, maxiter=60)
     assert iu["success"] and is_["success"] and iu["niter"] <= is_["niter"]
     assert np.abs(xu - xs).max() < 1e-8 * np.abs(xs).max()
+
+
+# ----------------------------------------------------------------------------- hierarchy (host side)
+@pytest.mark.parametrize("p,N,smoother,coarsen", [
+    (3, (16, 16), "glt", "semi"), (2, (8, 16, 8), "glt_poly", "semi"),
+    (3, (32, 8, 8), "glt_poly", "uniform"), (1, (16, 8), "glt", "semi"), (3, (16, 16, 16), "glt_poly", "semi")])
+def test_hierarchy_host_setup_matches_oracle(p, N, smoother, coarsen):
+    """Everything mg.Hierarchy computes on the host (grids, transfer rows, smoothing interval,
+    polynomial smoother factors) against the pinned oracle; no kernel runs, so no GPU is needed."""
+    from poms_b200.mg import Hierarchy
+    if smoother == "glt_poly" and p == 1:
+        pytest.skip("T[m_0] = I")
+    h = Hierarchy(p, list(N), Nc=4, device="cpu", smoother=smoother, coarsen=coarsen)
+    ho = po.MGHierarchy(p, list(N), Nc=4, smoother=smoother, coarsen=coarsen)
+    assert [lv.N for lv in h.levels] == [lv["N"] for lv in ho.levels]
+    for lv, lo in zip(h.levels[:-1], ho.levels[:-1]):
+        assert abs(lv.lmax - lo["lmax"]) < 1e-9 * lo["lmax"]
+        assert abs(lv.lmin - lo["lmin"]) < 1e-9 * lo["lmin"]
+        for a, rows in enumerate(lv.transfer.P1_rows):
+            if rows is None:
+                assert lo["P1s"][a].shape[0] == lo["P1s"][a].shape[1]
+                continue
+            st, cf, nc = rows
+            assert np.abs(bs.rows_to_dense(st, cf, nc) - lo["P1s"][a]).max() < 1e-14
+        if smoother == "glt_poly":
+            # S2 S1 = q3(T) per axis: the two band factors against the oracle's Horner polynomial
+            for a in range(len(N)):
+                T = po.band_to_dense(lo["gband"][a])
+                c = lo["qc"][a]
+                Q = sum(ck * np.linalg.matrix_power(T, k) for k, ck in enumerate(c))
+                F1 = bs.band_to_dense(lv.S1.Ms[a])
+                F2 = bs.band_to_dense(lv.S2.Ms[a])
+                assert np.abs(F2 @ F1 - Q).max() < 1e-10 * np.abs(Q).max()
+
+
+def test_hierarchy_coarsest_level_is_never_partitioned():
+    """With slabs the coarsest level is always replicated, whatever its size (its exact solve is a
+    replicated dense contraction), and a level is partitioned only while every rank keeps
+    min_planes planes."""
+    from poms_b200.mg import Hierarchy
+
+    class FakeSlab:                       # the constructor only reads size / rank / bounds
+        size, rank = 4, 1
+
+        def bounds(self, n, rank=None):
+            from poms_b200.dist import block_bounds
+            return block_bounds(n, self.size, self.rank if rank is None else rank)
+
+        def table(self, n):
+            from poms_b200.dist import block_bounds
+            return [block_bounds(n, self.size, r) for r in range(self.size)]
+
+    h = Hierarchy(3, [512, 16, 16], Nc=8, device="cpu", smoother="glt_poly", coarsen="uniform",
+                  slab=FakeSlab(), min_planes=32, lengths=[32.0, 1.0, 1.0])
+    assert [lv.N for lv in h.levels] == [[512, 16, 16], [256, 8, 8]]
+    assert [lv.distributed for lv in h.levels] == [True, False]
+    h = Hierarchy(3, [512, 16, 16], Nc=8, device="cpu", smoother="glt", coarsen="semi",
+                  slab=FakeSlab(), min_planes=32, lengths=[32.0, 1.0, 1.0])
+    flags = [lv.distributed for lv in h.levels]
+    assert flags[0] and not flags[-1] and flags == sorted(flags, reverse=True)
+    for lv in h.levels:
+        assert lv.distributed == (lv.V.slab is not None)
+        if lv.distributed:
+            assert lv.N[0] + 3 >= 4 * 32
+
+
+def test_no_compute_without_cuda():
+    """Host setup works anywhere; the first kernel call on a CPU space fails loudly."""
+    from poms_b200 import _lib
+    from poms_b200.mg import Hierarchy, vcycle
+    from poms_b200.stencil import StencilVector
+    h = Hierarchy(2, [8, 8], Nc=4, device="cpu")
+    b = StencilVector(h.levels[0].V)
+    with pytest.raises(_lib.PomsError):
+        vcycle(h, 0, b)
