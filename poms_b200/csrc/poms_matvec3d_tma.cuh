@@ -4,12 +4,15 @@
 // Per CTA: a 16 x 64 tile of axes (2,3), marching along axis 1.  For every input plane one elected
 // thread issues ONE cp.async.bulk.tensor.3d (TMA) that lands the halo'd (16+2p) x (64+2p) tile in a
 // shared-memory ring, zero-filled outside the domain by the hardware; an mbarrier signals arrival.
-// The ring is 4 deep: three planes of prefetch are in flight ahead of the consumer (one plane was
-// measured to leave the TMA latency exposed: 3.0 ms vs the generic kernel's 3.6 ms at 512^3).
+// The ring is 3 deep: two planes of prefetch are in flight ahead of the consumer (one plane was
+// measured to leave the TMA latency exposed: 3.0 ms vs the generic kernel's 3.6 ms at 512^3; a
+// fourth stage bought nothing and costs the second resident CTA).
 // su/sv (axis-3 results) are double-buffered, so there is ONE __syncthreads per plane.
-// Coefficients: axis 3 per-thread registers; axes 1 and 2 come from the kernel-parameter constant
-// bank when the rows involved are Toeplitz-interior (uniform knots: all but 2p rows per end),
-// otherwise from shared / global memory (CTA-uniform branch).
+// Coefficients come from the kernel-parameter constant bank for the Toeplitz-interior rows of
+// every axis (uniform knots: all but 2p rows per end).  The other rows: axis 3 -- the few boundary
+// column pairs of a tile are recomputed by a CTA-wide fix-up from global memory; axis 2 -- a
+// shared-memory table for the warps that hold boundary rows; axis 1 -- global memory on the few
+// boundary planes.  Measured at 515^3, p = 3, three terms + residual: 1.10 ms.
 #pragma once
 #include <cuda.h>
 #include <type_traits>
