@@ -39,7 +39,7 @@ for epi, name, nb in ((EPI_STORE, "store+dot", 16), (EPI_RESID, "resid", 24), (E
         ms = e0.elapsed_time(e1) / reps
         res[force] = ms
         print("%-10s %-8s %8.3f ms  %7.1f GB/s (alg %d B/DOF)  dot=%.15e" % (
-            name, {1: "generic", 0: "tma-wp", 2: "tma-blk"}[force], ms, nb * dof / ms / 1e6, nb, ctx.scal[20 + force].item()))
+            name, {1: "generic", 2: "tma"}[force], ms, nb * dof / ms / 1e6, nb, ctx.scal[20 + force].item()))
     diff = (y.data - y2.data).abs().max().item() / y.data.abs().max().item()
     print("   max rel diff generic vs tma: %.2e   speedup %.2fx" % (diff, res[1] / res[2]))
 L.poms_set_force_generic(0)

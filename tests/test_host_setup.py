@@ -185,3 +185,76 @@ def test_no_compute_without_cuda():
     b = StencilVector(h.levels[0].V)
     with pytest.raises(_lib.PomsError):
         vcycle(h, 0, b)
+
+
+# ----------------------------------------------------------------------------- kernel index models
+def test_matvec3d_tile_partition_model():
+    """Host model of the column-pair partition of kron_matvec3d_tma_kernel (poms_matvec3d_tma.cuh:
+    qb / tl / th): inside every 64-column tile each domain column belongs to exactly one pair, a
+    pair is either on the Toeplitz fast path (both columns interior rows of the band) or in the
+    boundary fix-up, never both, never neither -- for every degree, grid size and interior range."""
+    for p in (1, 2, 3, 4, 5):
+        sh = p & 1
+        for n3 in list(range(8, 140)) + [259, 515, 1027]:
+            ranges = [(0, 0), (0, n3), (n3 // 2, n3 // 2 + 1), (3, n3 - 1)]
+            if n3 - 2 * p >= 2 * p:
+                ranges.append((2 * p, n3 - 2 * p))
+            for lo3, hi3 in ranges:
+                cover = np.zeros(n3, dtype=int)
+                for bx in range((n3 + sh + 63) // 64):
+                    i3_0 = 64 * bx - sh
+                    qb = min(32, (n3 - i3_0 + 1) >> 1)
+                    tl = min(max((lo3 - i3_0 + 1) >> 1, 0), qb)
+                    th = min(max((hi3 - i3_0) >> 1, tl), qb)
+                    assert 0 <= tl <= th <= qb <= 32
+                    for q in range(qb):
+                        ca = i3_0 + 2 * q
+                        if tl <= q < th:                      # fast path: Toeplitz rows only
+                            assert lo3 <= ca and ca + 1 < hi3
+                        for c in (ca, ca + 1):
+                            if 0 <= c < n3:
+                                cover[c] += 1
+                    for q in range(qb, 32):                   # pairs beyond qb hold no domain column
+                        assert i3_0 + 2 * q >= n3
+                assert (cover == 1).all(), (p, n3, lo3, hi3)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5])
+def test_restrict3d_axis1_scatter_model(p):
+    """Host model of the axis-1 part of restrict3d_kernel (poms_transfer3d.cuh): marching over the
+    FINE planes of a chunk of coarse planes, scattering into at most RS_NS open partial sums and
+    emitting a coarse plane as soon as its last tap has passed -- against the dense R1."""
+    RS_NS = 6
+    for Nc, chunk in ((8, 8), (16, 8), (16, 5), (33, 8), (40, 64)):
+        nc, nf = Nc + p, 2 * Nc + p
+        st, cf, _ = bs.knot_insertion_rows(bs.make_open_knots(p, nc), bs.make_open_knots(p, nf), p)
+        s1, c1 = bs.rows_transpose(st, cf, nc)
+        W = c1.shape[1]
+        R = bs.rows_to_dense(st, cf, nc).T
+        # the host check of poms_restrict_3d: rows open at the same fine plane
+        lo, open_max = 0, 0
+        for i in range(nc):
+            while s1[lo] + W - 1 < s1[i]:
+                lo += 1
+            open_max = max(open_max, i - lo + 1)
+        assert open_max <= RS_NS
+        v = np.random.default_rng(p).standard_normal(nf)
+        out = np.full(nc, np.nan)
+        for i_lo in range(0, nc, chunk):
+            i_hi = min(nc, i_lo + chunk)
+            acc = [0.0] * RS_NS
+            i_cur = i_lo
+            j_hi = min(nf - 1, s1[i_hi - 1] + W - 1)
+            for j in range(s1[i_lo], j_hi + 1):
+                for s in range(RS_NS):
+                    i = i_cur + s
+                    if i < i_hi:
+                        t = j - s1[i]
+                        if 0 <= t < W:
+                            acc[s] += c1[i, t] * v[j]
+                while i_cur < i_hi and (s1[i_cur] + W - 1 <= j or j == j_hi):
+                    out[i_cur] = acc[0]
+                    acc = acc[1:] + [0.0]
+                    i_cur += 1
+            assert i_cur == i_hi
+        assert np.abs(out - R @ v).max() < 1e-13
