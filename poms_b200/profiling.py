@@ -48,5 +48,25 @@ def summary():
     return out
 
 
+def summary_largest(frac=0.5):
+    """Like summary(), restricted per kernel family to its LARGEST launches (declared bytes >= frac x
+    the family's maximum): the fine-level launches of a multigrid run, whose rate is the kernel's
+    roofline figure, without the latency-bound coarse-level launches of the same family."""
+    top = {}
+    for name, a, b, nbytes, launches in _records:
+        top[name] = max(top.get(name, 0), nbytes)
+    out = {}
+    for name, a, b, nbytes, launches in _records:
+        if nbytes <= 0 or nbytes < frac * top[name]:
+            continue
+        d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+        d["launches"] += launches
+        d["ms"] += a.elapsed_time(b)
+        d["bytes"] += nbytes
+    for d in out.values():
+        d["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+    return out
+
+
 def reset():
     del _records[:]

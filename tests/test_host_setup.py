@@ -339,3 +339,30 @@ def test_chunked_line_solve_plan_is_verified_on_the_host():
     # a warm-up that is too short must NOT pass the same check (the verification has teeth)
     assert np.abs(lu._emulate_chunked(y, chunk, 2) - ref).max() > 1e-10 * np.abs(ref).max()
     assert BandLU.from_band(bs.glt_band(p, 100, degree=5), "cpu").chunk_plan(100) is None   # short lines
+
+
+def test_profiling_summary_largest_selects_the_fine_level_launches():
+    from poms_b200 import profiling
+
+    class Ev:
+        def __init__(self, t):
+            self.t = t
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+
+    saved = list(profiling._records)
+    try:
+        del profiling._records[:]
+        # family "mv": two fine launches (1000 B, 1 ms each), one coarse (100 B, 0.5 ms); "dot": one
+        profiling._records += [("mv", Ev(0.0), Ev(1.0), 1000, 1), ("mv", Ev(1.0), Ev(1.5), 100, 1),
+                               ("mv", Ev(2.0), Ev(3.0), 900, 1), ("dot", Ev(0.0), Ev(0.25), 50, 1),
+                               ("exchange", Ev(0.0), Ev(0.1), 0, 1)]
+        full, fine = profiling.summary(), profiling.summary_largest()
+        assert full["mv"]["launches"] == 3 and abs(full["mv"]["ms"] - 2.5) < 1e-12
+        assert fine["mv"]["launches"] == 2 and abs(fine["mv"]["ms"] - 2.0) < 1e-12
+        assert fine["mv"]["bytes"] == 1900 and abs(fine["mv"]["gbs"] - 1900 / 2e-3 / 1e9) < 1e-15
+        assert fine["dot"]["launches"] == 1 and "exchange" not in fine
+    finally:
+        del profiling._records[:]
+        profiling._records += saved
