@@ -366,3 +366,37 @@ def test_profiling_summary_largest_selects_the_fine_level_launches():
     finally:
         del profiling._records[:]
         profiling._records += saved
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_bench_hierarchy_layout_per_rank(world):
+    """The weak-scaling bench's hierarchy (512^3 elements per GPU, uniform coarsening, coarsest 16)
+    built on the host for the first, an inner and the last rank: five partitioned levels with at
+    least 32 planes per rank, the coarsest replicated, and every partitioned transfer served by the
+    ghost planes (no slab copy)."""
+    from poms_b200.dist import block_bounds, ghost_view_range
+    from poms_b200.mg import Hierarchy
+
+    class FakeSlab:
+        def __init__(self, size, rank):
+            self.size, self.rank = size, rank
+
+        def bounds(self, n, rank=None):
+            return block_bounds(n, self.size, self.rank if rank is None else rank)
+
+        def table(self, n):
+            return [block_bounds(n, self.size, r) for r in range(self.size)]
+
+    for rank in sorted({0, world // 2, world - 1}):
+        h = Hierarchy(3, [512 * world, 512, 512], Nc=16, device="cpu", smoother="glt_poly",
+                      coarsen="uniform", slab=FakeSlab(world, rank), lengths=[float(world), 1.0, 1.0])
+        assert [lv.N[1] for lv in h.levels] == [512, 256, 128, 64, 32, 16]
+        assert [lv.distributed for lv in h.levels] == [True] * 5 + [False]
+        for lv in h.levels[:-1]:
+            V, tr = lv.V, lv.transfer
+            assert V.local_shape[0] >= 32 and V.pads[0] == 4            # 2q ghost planes for F2
+            assert ghost_view_range(tr.tf, tr.need_f, rank, V.pads[0], V.glo, V.local_shape[0])
+            if tr.cdist:
+                Vc = h.levels[h.levels.index(lv) + 1].V
+                assert ghost_view_range(tr.tc, tr.need_c, rank, Vc.pads[0], Vc.glo, Vc.local_shape[0])
+        assert h.levels[-1].V.local_shape[0] == 16 * world + 3
