@@ -96,7 +96,7 @@ class ClockSampler:
 _cpu_port = {}
 
 
-def cpu_port_solve(ndim, p, N, tol=1e-10, smoother="glt"):
+def cpu_port_solve(ndim, p, N, tol=1e-10, smoother="glt", Nc=8):
     """One MG-PCG solve with the CPU port of the same algorithm: oracle/poms_oracle_mt.py (numba,
     all host threads), or the single-threaded NumPy oracle if numba is unavailable.  b = A x0 like
     the GPU arm.  Returns (dof, seconds, info, cores, label)."""
@@ -112,7 +112,8 @@ def cpu_port_solve(ndim, p, N, tol=1e-10, smoother="glt"):
             from oracle import poms_oracle as po
             _cpu_port.update(mod=po, cls=po.MGHierarchy, cores=1,
                              label="NumPy/SciPy oracle, single thread (numba unavailable: %s)" % exc)
-    h = _cpu_port["cls"](p, [N] * ndim, smoother=smoother, nu=1)
+    # same hierarchy rule as the GPU arm: uniform coarsening down to Nc elements per axis
+    h = _cpu_port["cls"](p, [N] * ndim, smoother=smoother, nu=1, Nc=Nc, coarsen="uniform")
     A = h.levels[0]["A"]
     x0 = np.zeros(A.npts)
     for a in range(ndim):
@@ -281,12 +282,11 @@ def main():
 
     for _ in range(args.warmup):
         x, info = solve()
-    # ---- timed region: K solves, device-resident inputs --------------------------------------
+    # ---- timed region: K solves, device-resident inputs, NO per-kernel instrumentation ---------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    if not args.no_kernel_timing:
-        profiling.enable(True)
+    profiling.enable(False)
     barrier()
     l0 = L.poms_launch_count()
     e0 = torch.cuda.Event(enable_timing=True)
@@ -298,13 +298,27 @@ def main():
     barrier()
     launches = L.poms_launch_count() - l0
     ms = e0.elapsed_time(e1) / args.steps
-    kern = profiling.summary() if profiling.enabled() else {}
-    try:
-        kern_fine = profiling.summary_largest() if profiling.enabled() else {}
-    except Exception:                        # informational only
-        kern_fine = {}
-    profiling.enable(False)
     clocks = sampler.stop() if rank == 0 else None
+    # ---- separate instrumented pass (CUDA events around every kernel family) for the roofline and
+    # the per-kernel breakdown: its event records perturb the latency-bound coarse levels, so it
+    # is kept out of the headline timing above
+    kern, kern_fine, prof_steps, ms_prof = {}, {}, 0, 0.0
+    if not args.no_kernel_timing:
+        prof_steps = min(args.steps, 3)
+        profiling.enable(True)
+        barrier()
+        e0.record()
+        for _ in range(prof_steps):
+            solve()
+        e1.record()
+        barrier()
+        ms_prof = e0.elapsed_time(e1) / prof_steps
+        kern = profiling.summary()
+        try:
+            kern_fine = profiling.summary_largest()
+        except Exception:                        # informational only
+            kern_fine = {}
+        profiling.enable(False)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -345,7 +359,8 @@ def main():
         return
 
     peak, peak_src = measured_peaks()
-    steps = args.steps
+    steps = max(prof_steps, 1)
+    ms_headline, ms = ms, (ms_prof if prof_steps else ms)      # shares refer to the instrumented pass
     for d in kern.values():
         d["ms_per_step"] = d["ms"] / steps
         d["share"] = d["ms"] / (ms * steps) if ms > 0 else 0.0
@@ -376,6 +391,7 @@ def main():
                                   "launches": kf["launches"],
                                   "avg_launch_ms": kf["ms"] / kf["launches"],
                                   "share_of_step": kf["ms"] / (ms * steps) if ms > 0 else 0.0}
+    ms = ms_headline
     line = {
         "metric": METRIC, "value": dof_global / (ms * 1e-3), "unit": "DOF/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -413,7 +429,7 @@ def main():
         # the CPU port has the two GLT smoothers only
         smo = "glt" if args.smoother == "jacobi" else args.smoother
         try:
-            dofc, dtc, infoc, cores, label = cpu_port_solve(ndim, p, Ns_cpu, smoother=smo)
+            dofc, dtc, infoc, cores, label = cpu_port_solve(ndim, p, Ns_cpu, smoother=smo, Nc=Nc)
             line["cpu_baseline"] = {
                 "value": dofc / dtc, "unit": "DOF/s", "cores": cores, "kind": "port",
                 "host_cores_available": os.cpu_count(),

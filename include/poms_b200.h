@@ -33,6 +33,8 @@ int64_t poms_workspace_bytes(void);
 const char* poms_last_error(void);
 /* number of kernel launches issued through this library since load (bench "gpu_launches") */
 int64_t poms_launch_count(void);
+/* kernels replayed from a captured CUDA graph are not seen by the library: the caller adds them */
+void poms_launch_count_add(int64_t n);
 
 /* operator forms for poms_kron_matvec_* */
 #define POMS_FORM_SINGLE 0 /* Y = (A1 (x) A2 [(x) A3]) X; the A's are passed in the m* slots   */
@@ -84,6 +86,9 @@ int poms_kron_matvec_3d_ex(const double* x, double* y, const double* b,
 void poms_set_force_generic(int flag);
 /* A/B timing only: fix the axis-1 chunk (planes per CTA) of the 3-D mat-vec; 0 = automatic. */
 void poms_set_matvec3d_chunk(int chunk);
+/* Kernel variant of the TMA path: 1 = anti-phase pipeline (default), 0 = round-1 kernel (one stage at a
+ * time); initial value from the environment variable POMS_B200_MV3_VARIANT.  A/B timing and tests. */
+void poms_set_matvec3d_variant(int variant);
 
 /*
  * Full (non-separable) 2-D stencil mat-vec: y[i1,i2] = sum_{k1,k2} S[i1,i2,k1,k2] x[i1+k1-p1,i2+k2-p2]

@@ -13,6 +13,7 @@ _PROTOS = {
     "poms_workspace_bytes": (_l, []),
     "poms_last_error": (C.c_char_p, []),
     "poms_launch_count": (_l, []),
+    "poms_launch_count_add": (None, [_l]),
     "poms_kron_matvec_2d": (C.c_int, [_vp, _vp, _vp, _i, _i, _l, _i, _i, _i, _i,
                                      _vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp]),
     "poms_kron_matvec_3d": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _i,
@@ -22,6 +23,7 @@ _PROTOS = {
                                         _vp, _vp]),
     "poms_set_force_generic": (None, [_i]),
     "poms_set_matvec3d_chunk": (None, [_i]),
+    "poms_set_matvec3d_variant": (None, [_i]),
     "poms_stencil_matvec_2d": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _l, _i, _i, _i, _i,
                                         _i, _d, _vp, _vp, _vp]),
     "poms_cg_update": (C.c_int, [_vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp]),

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "poms_b200.h"
 
 #define POMS_MAX_PARTIALS 65536
@@ -41,6 +42,7 @@ extern "C" int64_t poms_workspace_bytes(void) {
 }
 extern "C" const char* poms_last_error(void) { return g_err; }
 extern "C" int64_t poms_launch_count(void) { return g_launches; }
+extern "C" void poms_launch_count_add(int64_t n) { g_launches += n; }
 
 // ------------------------------------------------------------------------------------------
 // cp.async helpers (Ampere-style asynchronous global -> shared copies, 8 bytes per thread)

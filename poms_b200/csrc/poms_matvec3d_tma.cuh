@@ -408,6 +408,10 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 }
 
 // ---- host side -----------------------------------------------------------------------------
+#include "poms_matvec3d_pipe.cuh"
+#include <unordered_map>
+#include <mutex>
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -425,34 +429,88 @@ static PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
-template <int P, int FORM, int EPI>
+// Tensor maps are pure functions of (base address, extents, pitches, box): the V-cycle applies the
+// same few operators to the same few vectors thousands of times, so the encoded descriptors are kept
+// (round 1 re-encoded one per launch on the host, 576 times per solve).
+struct TmapKey {
+    uint64_t addr, n3, n2, n1, ld, pld, box;
+    bool operator==(const TmapKey& o) const {
+        return addr == o.addr && n3 == o.n3 && n2 == o.n2 && n1 == o.n1 && ld == o.ld && pld == o.pld && box == o.box;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t h = 1469598103934665603ull;
+        const uint64_t v[7] = {k.addr, k.n3, k.n2, k.n1, k.ld, k.pld, k.box};
+        for (int i = 0; i < 7; ++i) { h ^= v[i]; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+static int get_tmap(PFN_encodeTiled enc, const double* base, int n3, int n2, int n1tot, int64_t ld, int64_t pld,
+                    int boxw, int boxh, CUtensorMap* out) {
+    static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    static std::mutex mu;
+    const TmapKey key{(uint64_t)(uintptr_t)base, (uint64_t)n3, (uint64_t)n2, (uint64_t)n1tot, (uint64_t)ld,
+                      (uint64_t)pld, ((uint64_t)boxw << 32) | (uint64_t)boxh};
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+    cuuint64_t dims[3] = {(cuuint64_t)n3, (cuuint64_t)n2, (cuuint64_t)n1tot};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)pld * 8};
+    cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 1;
+    if (cache.size() > 4096) cache.clear();   // addresses of freed temporaries: bounded, not LRU
+    cache.emplace(key, *out);
+    return 0;
+}
+
+// kernel variant: 1 = anti-phase pipeline (round 2, default), 0 = round-1 kernel (A/B timing, tests)
+static int g_mv3_variant = -1;
+extern "C" void poms_set_matvec3d_variant(int v) { g_mv3_variant = v; }
+static int mv3_variant() {
+    if (g_mv3_variant < 0) {
+        const char* e = getenv("POMS_B200_MV3_VARIANT");
+        g_mv3_variant = e ? atoi(e) : 1;
+    }
+    return g_mv3_variant;
+}
+
+template <int P, int FORM, int EPI, int VAR>
 static int launch_mv3_tma_inst(const CUtensorMap& tm, const MV3T& g, dim3 grid, cudaStream_t st) {
     const size_t smem = MV3TCfg<P>::smem_bytes(FORM == POMS_FORM_SUM);
+    auto kern = VAR == 0 ? kron_matvec3d_tma_kernel<P, FORM, EPI> : kron_matvec3d_pipe_kernel<P, FORM, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kron_matvec3d_tma_kernel<P, FORM, EPI>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(tma)");
         attr_set = true;
     }
-    kron_matvec3d_tma_kernel<P, FORM, EPI><<<grid, 256, smem, st>>>(tm, g);
+    kern<<<grid, 256, smem, st>>>(tm, g);
     return 0;
 }
-template <int P, int FORM>
+template <int P, int FORM, int VAR>
 static int launch_mv3_tma_epi(const CUtensorMap& tm, const MV3T& g, int epi, dim3 grid, cudaStream_t st) {
     switch (epi) {
-        case POMS_EPI_STORE: return launch_mv3_tma_inst<P, FORM, POMS_EPI_STORE>(tm, g, grid, st);
-        case POMS_EPI_RESID: return launch_mv3_tma_inst<P, FORM, POMS_EPI_RESID>(tm, g, grid, st);
-        case POMS_EPI_JACOBI: return launch_mv3_tma_inst<P, FORM, POMS_EPI_JACOBI>(tm, g, grid, st);
-        case POMS_EPI_DINV: return launch_mv3_tma_inst<P, FORM, POMS_EPI_DINV>(tm, g, grid, st);
-        case POMS_EPI_AXPY: return launch_mv3_tma_inst<P, FORM, POMS_EPI_AXPY>(tm, g, grid, st);
+        case POMS_EPI_STORE: return launch_mv3_tma_inst<P, FORM, POMS_EPI_STORE, VAR>(tm, g, grid, st);
+        case POMS_EPI_RESID: return launch_mv3_tma_inst<P, FORM, POMS_EPI_RESID, VAR>(tm, g, grid, st);
+        case POMS_EPI_JACOBI: return launch_mv3_tma_inst<P, FORM, POMS_EPI_JACOBI, VAR>(tm, g, grid, st);
+        case POMS_EPI_DINV: return launch_mv3_tma_inst<P, FORM, POMS_EPI_DINV, VAR>(tm, g, grid, st);
+        case POMS_EPI_AXPY: return launch_mv3_tma_inst<P, FORM, POMS_EPI_AXPY, VAR>(tm, g, grid, st);
         default: return bad_arg(19, "epilogue");
     }
 }
 template <int P>
 static int launch_mv3_tma(const CUtensorMap& tm, const MV3T& g, int form, int epi, dim3 grid, cudaStream_t st) {
-    if (form == POMS_FORM_SINGLE) return launch_mv3_tma_epi<P, POMS_FORM_SINGLE>(tm, g, epi, grid, st);
-    return launch_mv3_tma_epi<P, POMS_FORM_SUM>(tm, g, epi, grid, st);
+    if (mv3_variant() == 0) {
+        if (form == POMS_FORM_SINGLE) return launch_mv3_tma_epi<P, POMS_FORM_SINGLE, 0>(tm, g, epi, grid, st);
+        return launch_mv3_tma_epi<P, POMS_FORM_SUM, 0>(tm, g, epi, grid, st);
+    }
+    if (form == POMS_FORM_SINGLE) return launch_mv3_tma_epi<P, POMS_FORM_SINGLE, 1>(tm, g, epi, grid, st);
+    return launch_mv3_tma_epi<P, POMS_FORM_SUM, 1>(tm, g, epi, grid, st);
 }
 
 // returns 0 on success, 1 if the TMA path does not apply (caller falls back to the generic kernel),
@@ -492,16 +550,9 @@ static int try_matvec3d_tma(const MV3& a0, int p, int form, int epilogue, const 
     const int g1 = (a0.n1 + g.a.chunk - 1) / g.a.chunk;
     if ((int64_t)g3 * g2 * g1 > POMS_MAX_PARTIALS) return 1;
     CUtensorMap tm;
-    cuuint64_t dims[3] = {(cuuint64_t)a0.n3, (cuuint64_t)a0.n2, (cuuint64_t)(a0.n1 + a0.glo + a0.ghi)};
-    cuuint64_t strides[2] = {(cuuint64_t)a0.ld * 8, (cuuint64_t)a0.pld * 8};
-    const int boxw = 64 + 2 * p + 2 * sh;
-    cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)(16 + 2 * p), 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    void* gaddr = (void*)(a0.x - (int64_t)a0.glo * a0.pld);
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, gaddr, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return 1;
+    if (get_tmap(enc, a0.x - (int64_t)a0.glo * a0.pld, a0.n3, a0.n2, a0.n1 + a0.glo + a0.ghi, a0.ld, a0.pld,
+                 64 + 2 * p + 2 * sh, 16 + 2 * p, &tm))
+        return 1;
     dim3 grid(g3, g2, g1);
     int rc;
     switch (p) {

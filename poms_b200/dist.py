@@ -324,16 +324,16 @@ def spike_solve_host(setup, y_blocks):
     return out
 
 
-_spike_cache = {}
-
-
 def _spike_for(lu, V):
     """SPIKE setup + device operators of one axis-1 factor for the partition of space V (cached)."""
     from .kron_product import BandLU
     from .mg import _AxisOp
     slab = V.slab
-    key = (id(lu), V.npts[0], slab.size, slab.rank, str(V.device))
-    ent = _spike_cache.get(key)
+    # the cache lives ON the factor object: an id()-keyed module cache would hand a stale setup to a
+    # new BandLU that happens to reuse the id of a freed one
+    cache = lu.__dict__.setdefault("_spike", {})
+    key = (V.npts[0], slab.size, slab.rank, str(V.device))
+    ent = cache.get(key)
     if ent is not None:
         return ent
     if getattr(lu, "band", None) is None:
@@ -378,7 +378,7 @@ def _spike_for(lu, V):
     if r < G - 1 and st.mV[r] > 0:
         m = st.mV[r]
         ent["corrV"] = (_AxisOp(np.zeros(m, dtype=np.int32), -st.V[r][nl - m:], q, dev), m)
-    _spike_cache[key] = ent
+    cache[key] = ent
     return ent
 
 

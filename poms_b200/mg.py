@@ -152,15 +152,26 @@ class Transfer:
         # where the three streaming passes run closer to the HBM rate than the fused tile pipeline)
         self.fused = self.ndim == 3 and all(op is not None for op in self.P)
         self.fused_max = 6_000_000      # fine points per rank up to which the fused kernels are used
+        self._tmps = {}
 
     def _want_fused(self, shape_f):
         return self.fused and int(np.prod(shape_f)) <= self.fused_max
 
-    def restrict(self, rf, Vc):
+    def _tmp(self, key, shape, ld):
+        """Intermediate array of a per-axis pass, allocated (and zeroed: pad column) once per
+        transfer object and reused by every later application."""
+        k = (key, tuple(shape), ld)
+        t = self._tmps.get(k)
+        if t is None:
+            t = self._tmps[k] = _tmp(shape, ld, self.device, zero=True)
+        return t
+
+    def restrict(self, rf, Vc, out=None):
         """r_c = (P1^T (x) .. (x) P1^T) r_f.  Axis 1 first: the largest array is read once,
-        fully coalesced, and every later pass works on a smaller one."""
+        fully coalesced, and every later pass works on a smaller one.  `out`: vector of Vc that
+        receives the result (its pad column must be zero), default a new one."""
         assert rf.space.slab is None or rf.space.slab.size == 1, "use DistTransfer for slabs"
-        rc = StencilVector(Vc)
+        rc = StencilVector(Vc) if out is None else out
         cur, ld = rf.flat, rf.ld
         shape = tuple(rf.space.local_shape)
         if self._want_fused(shape):
@@ -177,7 +188,7 @@ class Transfer:
             shape_out[ax] = op.n_out
             last = n == len(ops) - 1
             ld_out = _pitch(op.n_out) if ax == nd - 1 else ld
-            dst = rc.flat if last else _tmp(shape_out, ld_out, self.device, zero=(ax == nd - 1))
+            dst = rc.flat if last else self._tmp(("R", n), shape_out, ld_out)
             if last:
                 assert ld_out == rc.ld
             shape = op.apply(cur, dst, shape, ld, ld_out, ax)
@@ -204,7 +215,7 @@ class Transfer:
             shape_out[ax] = op.n_out
             last = n == len(ops) - 1
             ld_out = _pitch(op.n_out) if ax == nd - 1 else ld
-            dst = xf.flat if last else _tmp(shape_out, ld_out, self.device, zero=(ax == nd - 1))
+            dst = xf.flat if last else self._tmp(("P", n), shape_out, ld_out)
             if last:
                 assert ld_out == xf.ld
             shape = op.apply(cur, dst, shape, ld, ld_out, ax, accumulate=last)
@@ -247,7 +258,7 @@ class DistTransfer(Transfer):
         self.slab.exchange(v)
         return v._buf[rng[0]:rng[1]]
 
-    def restrict(self, rf, Vc):
+    def restrict(self, rf, Vc, out=None):
         slab = self.slab
         nd = len(rf.space.local_shape)
         ld = rf.ld
@@ -259,7 +270,7 @@ class DistTransfer(Transfer):
             planes = slab.gather_planes(rf.flat, self.tf, self.need_f)
         shape_f = (planes.shape[0],) + tuple(rf.space.local_shape[1:])
         if self._want_fused(shape_f):
-            rc = StencilVector(Vc)
+            rc = StencilVector(Vc) if out is None else out
             shape_c = (ce - cs + 1,) + tuple(Vc.local_shape[1:])
             dst = rc.flat if self.cdist else _tmp(shape_c, rc.ld, self.device)
             if _fused_restrict((self.R0, self.R[1], self.R[2]), planes, shape_f, ld, dst, shape_c,
@@ -270,7 +281,7 @@ class DistTransfer(Transfer):
             self.fused = False
         shape = (planes.shape[0],) + tuple(rf.space.local_shape[1:])
         ops = [(ax, op) for ax, op in enumerate(self.R) if op is not None and ax > 0]
-        rc = StencilVector(Vc)
+        rc = StencilVector(Vc) if out is None else out
         own_view = rc.flat if self.cdist else None
         # axis 1 (slab axis)
         last = not ops
@@ -363,13 +374,14 @@ class CoarseSolver:
         self.D = torch.as_tensor(np.ascontiguousarray(Dp), device=device)
         self.device = device
 
-    def solve(self, b):
-        """x = A^-1 b (new vector)."""
+    def solve(self, b, out=None):
+        """x = A^-1 b (a new vector, or `out`)."""
         V = b.space
         shape = tuple(V.local_shape)
         ld = V.ld
-        t0 = _tmp(shape, ld, self.device)
-        t1 = _tmp(shape, ld, self.device)
+        if getattr(self, "_t", None) is None:
+            self._t = (_tmp(shape, ld, self.device), _tmp(shape, ld, self.device))
+        t0, t1 = self._t
         cur = b.flat
         bufs = [t0, t1]
         for a in range(self.ndim):
@@ -382,7 +394,7 @@ class CoarseSolver:
                                                cur.numel(), 1.0, None, ctx.ws_ptr, _stream()),
                    "poms_diag_scale")
         cur = other
-        x = StencilVector(V)
+        x = StencilVector(V) if out is None else out
         for a in range(self.ndim):
             last = a == self.ndim - 1
             dst = x.flat if last else (t0 if cur is t1 else t1)
@@ -460,7 +472,15 @@ def _gen_eig_max(Kb, Tb):
 
 
 class Level:
-    pass
+    def ws(self, name):
+        """Persistent work vector of this level (zero-initialised once, then reused by every cycle):
+        no allocation, no memset and stable device addresses inside the V-cycle, which is what lets
+        the cycle be captured in a CUDA graph."""
+        d = self.__dict__.setdefault("_ws", {})
+        v = d.get(name)
+        if v is None:
+            v = d[name] = StencilVector(self.V)
+        return v
 
 
 class Hierarchy:
@@ -569,15 +589,16 @@ class Hierarchy:
         V = lv.V
         ctx = DeviceContext.get(self.device)
         g = torch.Generator(device="cpu").manual_seed(1234)
+        # from_array keeps the owned planes of the (identical on every rank) global start vector
         v = StencilVector.from_array(V, torch.rand(V.npts, generator=g, dtype=torch.float64)
-                                     .numpy() + 0.5) if V.slab is None else None
+                                     .numpy() + 0.5)
         zero = StencilVector(V)
         w = StencilVector(V)
         lam = 1.0
         for _ in range(iters):
             # w = -D^-1 (0 - A v) = D^-1 A v
             lv.A.apply(v, w, EPI_DINV, b=zero, omega=-1.0, dot_ptr=ctx.sptr(solvers.S_TMP))
-            nw = sqrt(float(ctx.scal[solvers.S_TMP].item()))
+            nw = sqrt(solvers._read(ctx, V, solvers.S_TMP))    # all-reduced over the slabs
             nv = sqrt(v.dot(v))
             lam = nw / nv
             v = w * (1.0 / nw)
@@ -595,12 +616,12 @@ class Hierarchy:
         rho = 1.0 / sigma
         if self.smoother == "glt_poly":
             # nu Richardson steps x <- x + (1/theta) S2 S1 (b - A x): three fused Kronecker passes
-            t1 = StencilVector(V, zero=False)
+            t1 = lv.ws("t1")
             for k in range(self.nu):
                 if k == 0 and zero_guess:
                     src = b
                 else:
-                    r = StencilVector(V, zero=False)
+                    r = lv.ws("r")
                     A.apply(x, r, EPI_RESID, b=b)
                     src = r
                 lv.S1.apply(src, t1, EPI_STORE)
@@ -613,17 +634,17 @@ class Hierarchy:
         if self.smoother == "glt" and self.nu == 1 and all(lu.nopiv for lu in lv.glt_lu):
             # one step: x <- x + (1/theta) B^-1 (b - A x); the update is fused into the last line
             # solve (d = c1*d + c2*z with c1 = 0, so x + d == x + c2*z)
-            work = StencilVector(V, zero=False)
+            work = lv.ws("t1")
             if zero_guess:
                 kron_solve_bnd_update(lv.glt_lu, b, work, x, 1.0 / theta)
             else:
-                r = StencilVector(V, zero=False)
+                r = lv.ws("r")
                 A.apply(x, r, EPI_RESID, b=b)
                 kron_solve_bnd_update(lv.glt_lu, r, work, x, 1.0 / theta, add=x)
             return x
-        r = StencilVector(V, zero=False)
-        z = StencilVector(V, zero=False) if self.smoother == "glt" else r
-        d = StencilVector(V, zero=False)      # written (c1 = 0) by the first Chebyshev step
+        r = lv.ws("r")
+        z = lv.ws("t1") if self.smoother == "glt" else r
+        d = lv.ws("d")                        # written (c1 = 0) by the first Chebyshev step
         for k in range(self.nu):
             if self.smoother == "glt":
                 if k == 0 and zero_guess:
@@ -650,17 +671,22 @@ class Hierarchy:
 
 
 def vcycle(h, l, b):
-    """One V(nu,nu) cycle from a zero initial guess on level l; returns a new vector."""
+    """One V(nu,nu) cycle from a zero initial guess on level l.  Returns the level's persistent
+    solution vector `lv.ws("x")`: it is overwritten by the next cycle, copy it to keep it."""
     lv = h.levels[l]
     if l == len(h.levels) - 1:
-        return h.coarse.solve(b)
-    # the polynomial smoother overwrites x on a zero guess; the others accumulate into it
-    x = StencilVector(lv.V, zero=(h.smoother != "glt_poly"))
+        return h.coarse.solve(b, out=lv.ws("x"))
+    x = lv.ws("x")
+    # the polynomial smoother and the fused GLT update overwrite x on a zero guess; the Chebyshev
+    # recurrences accumulate into it
+    if not (h.smoother == "glt_poly" or (h.smoother == "glt" and h.nu == 1
+                                         and all(lu.nopiv for lu in lv.glt_lu))):
+        x.flat.zero_()
     h.smooth(lv, b, x, True)
-    r = StencilVector(lv.V, zero=False)
+    r = lv.ws("r")
     lv.A.apply(x, r, EPI_RESID, b=b)
     with profiling.region("restrict", 8 * lv.V.local_size, launches=h.ndim):
-        rc = lv.transfer.restrict(r, h.levels[l + 1].V)
+        rc = lv.transfer.restrict(r, h.levels[l + 1].V, out=h.levels[l + 1].ws("b"))
     ec = vcycle(h, l + 1, rc)
     with profiling.region("prolong_add", 16 * lv.V.local_size, launches=h.ndim):
         lv.transfer.prolong_add(ec, x)
@@ -668,11 +694,134 @@ def vcycle(h, l, b):
     return x
 
 
+def _graphs_wanted(h, b):
+    """CUDA graphs for the PCG iteration: one device, no per-kernel instrumentation, not disabled."""
+    import os
+    V = b.space
+    return (os.environ.get("POMS_B200_GRAPH", "1") != "0" and not profiling.enabled()
+            and (V.slab is None or V.slab.size == 1) and V.compatible(h.levels[0].V)
+            and V.pads == h.levels[0].V.pads)
+
+
+class _PcgGraphs:
+    """Persistent PCG state of one hierarchy (x, r, p, q on the fine level) and the two CUDA graphs of
+    an iteration of /root/reference/sources/solvers.py:101-124 with the V-cycle as psolve:
+        G1: q = A p ; p.q ; x += alpha p ; r -= alpha q ; r.r          (lines 103-111)
+        G2: s = V-cycle(r) ; s.r ; p = s + beta p ; sr_old = sr         (lines 117-124)
+    The break test between them (line 113) reads one scalar on the host.  The launch sequence of a
+    hierarchy is fixed and alpha / beta already live on the device, so the ~60 (C5) to ~90 launches of
+    an iteration become two graph launches: the coarse levels stop being launch-latency bound."""
+
+    def __init__(self, h):
+        from .solvers import S_RR, S_PQ, S_SR0, S_SR1
+        lv = h.levels[0]
+        self.h = h
+        self.x, self.r, self.p, self.q = (lv.ws(n) for n in ("pcg_x", "pcg_r", "pcg_p", "pcg_q"))
+        self.ctx = DeviceContext.get(h.device)
+        self.S_OLD, self.S_NEW = S_SR0, S_SR1
+        L = _lib.lib()
+        # eager dry run: creates every work vector, tensor map and function attribute, then capture
+        self.r.flat.fill_(1.0)
+        self.p.flat.zero_()
+        self.x.flat.zero_()
+        self.ctx.scal[self.S_OLD] = 1.0
+        self._g2_body()
+        self._g1_body()
+        torch.cuda.synchronize()
+        self.g1, self.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        n0 = L.poms_launch_count()
+        with torch.cuda.graph(self.g1):
+            self._g1_body()
+        n1 = L.poms_launch_count()
+        with torch.cuda.graph(self.g2):
+            self._g2_body()
+        self.n_g1, self.n_g2 = n1 - n0, L.poms_launch_count() - n1
+        self.pad_clean()
+
+    def pad_clean(self):
+        for v in (self.x, self.r, self.p, self.q):
+            V = v.space
+            if V.ld != V.local_shape[-1]:
+                v._buf[..., V.local_shape[-1]:] = 0.0
+
+    def _g1_body(self):
+        from .solvers import S_RR, S_PQ
+        A, ctx, L = self.h.levels[0].A, self.ctx, _lib.lib()
+        A.apply(self.p, self.q, EPI_STORE, dot_ptr=ctx.sptr(S_PQ))
+        _lib.check(L.poms_cg_update(self.x.ptr, self.r.ptr, self.p.ptr, self.q.ptr, self.x.n_owned,
+                                    ctx.sptr(self.S_OLD), ctx.sptr(S_PQ), ctx.sptr(S_RR), ctx.ws_ptr,
+                                    _stream()), "poms_cg_update")
+
+    def _g2_body(self):
+        from .stencil import dot_into
+        ctx, L = self.ctx, _lib.lib()
+        s = vcycle(self.h, 0, self.r)
+        dot_into(s, self.r, ctx.sptr(self.S_NEW), ctx)
+        _lib.check(L.poms_p_update(self.p.ptr, s.ptr, self.p.n_owned, ctx.sptr(self.S_NEW),
+                                   ctx.sptr(self.S_OLD), _stream()), "poms_p_update")
+        ctx.scal[self.S_OLD:self.S_OLD + 1].copy_(ctx.scal[self.S_NEW:self.S_NEW + 1])
+
+    def run_g1(self):
+        self.g1.replay()
+        _lib.lib().poms_launch_count_add(self.n_g1)
+
+    def run_g2(self):
+        self.g2.replay()
+        _lib.lib().poms_launch_count_add(self.n_g2)
+
+
+def _pcg_graphed(h, b, x0, tol, maxiter, abs_thresh=None):
+    """`solvers._pcg_driver(relative=True)` on the persistent state of `_PcgGraphs` (same operations,
+    same order, same device scalars; p = s is realised as p = s + beta*0)."""
+    from .solvers import S_RR
+    from .stencil import dot_into
+    g = h.__dict__.get("_pcg_graphs")
+    if g is None:
+        g = h._pcg_graphs = _PcgGraphs(h)
+    ctx, A = g.ctx, h.levels[0].A
+    x, r, p = g.x, g.r, g.p
+    if x0 is None:
+        x.flat.zero_()
+        r.flat.copy_(b.flat)
+        dot_into(r, r, ctx.sptr(S_RR), ctx)
+    else:
+        if x0 is not x:
+            x.flat.copy_(x0.flat)
+        A.apply(x, r, EPI_RESID, b=b, dot_ptr=ctx.sptr(S_RR))
+    nrmr0 = sqrt(float(ctx.scal[S_RR].item()))
+    thresh = (tol * nrmr0) ** 2
+    if abs_thresh is not None:
+        thresh = abs_thresh
+        if nrmr0 * nrmr0 <= thresh:
+            return x, {"niter": 0, "success": True, "res_norm": nrmr0, "history": [],
+                       "res_norm0": nrmr0}
+    p.flat.zero_()
+    ctx.scal[g.S_OLD] = 1.0
+    g.run_g2()                       # s = psolve(r); p = s; sr
+    hist = []
+    k = 0
+    nrmr = nrmr0 * nrmr0
+    for k in range(1, maxiter + 1):
+        g.run_g1()
+        nrmr = float(ctx.scal[S_RR].item())
+        hist.append(sqrt(nrmr))
+        if nrmr <= thresh:
+            k -= 1
+            break
+        g.run_g2()
+    info = {"niter": k, "success": bool(nrmr <= thresh), "res_norm": sqrt(nrmr), "history": hist,
+            "res_norm0": nrmr0}
+    return x, info
+
+
 def mg_pcg(h, b, x0=None, tol=1e-10, maxiter=200, criterion="relative", verbose=False,
            max_restarts=3):
     """MG-preconditioned CG: the reference's `pcg` driver (same operation order) with one V-cycle
     as `psolve`.  criterion='relative': stop when ||r|| <= tol*||r0|| (the BASELINE metric);
-    criterion='reference': the reference's own mixed rule r.r < tol*||r0||."""
+    criterion='reference': the reference's own mixed rule r.r < tol*||r0||.
+    On one device the iteration runs as two CUDA graphs (`_PcgGraphs`; POMS_B200_GRAPH=0 or an
+    enabled profiler selects the launch-by-launch driver); the returned x is then the hierarchy's
+    persistent solution vector, overwritten by the next solve on the same hierarchy."""
     A = h.levels[0].A
 
     def psolve(A_, r):
@@ -680,16 +829,22 @@ def mg_pcg(h, b, x0=None, tol=1e-10, maxiter=200, criterion="relative", verbose=
 
     if criterion == "reference":
         return solvers.pcg(A, psolve, b, x0=x0, tol=tol, maxiter=maxiter, verbose=verbose)
-    x, info = solvers._pcg_driver(A, psolve, b, x0, tol, maxiter, verbose, "MG-PCG solver:",
-                                  relative=True)
+    graphed = _graphs_wanted(h, b) and not verbose
+
+    def drive(x0_, tol_, maxiter_, title, abs_thresh=None):
+        if graphed:
+            return _pcg_graphed(h, b, x0_, tol_, maxiter_, abs_thresh=abs_thresh)
+        return solvers._pcg_driver(A, psolve, b, x0_, tol_, maxiter_, verbose, title,
+                                   relative=True, abs_thresh=abs_thresh)
+
+    x, info = drive(x0, tol, maxiter, "MG-PCG solver:")
     # The CG recurrence residual drifts from b - A x on ill-conditioned problems (2-D 2048^2: 1e-10
     # claimed, 9e-10 true).  Verify with the TRUE residual and restart from x until it meets the
     # target (each restart recomputes r = b - A x; it returns at once when the target is met).
     target = (tol * info["res_norm0"]) ** 2
     info["restarts"] = 0
     while info["restarts"] < max_restarts and info["niter"] < maxiter:
-        x2, i2 = solvers._pcg_driver(A, psolve, b, x, tol, maxiter - info["niter"], verbose,
-                                     "MG-PCG restart:", relative=True, abs_thresh=target)
+        x2, i2 = drive(x, tol, maxiter - info["niter"], "MG-PCG restart:", abs_thresh=target)
         info["res_norm"] = i2["res_norm"] if i2["niter"] else i2["res_norm0"]
         info["true_res_norm"] = i2["res_norm0"] if not i2["niter"] else None
         if i2["niter"] == 0:
@@ -699,4 +854,5 @@ def mg_pcg(h, b, x0=None, tol=1e-10, maxiter=200, criterion="relative", verbose=
         info["history"] = list(info["history"]) + list(i2["history"])
         info["restarts"] += 1
     info["success"] = bool(info["res_norm"] ** 2 <= target)
+    info["graphed"] = bool(graphed)
     return x, info

@@ -77,7 +77,10 @@ def _pcg_driver(A, psolve, b, x0, tol, maxiter, verbose, title, relative=False, 
             return x, {"niter": 0, "success": True, "res_norm": nrmr0, "history": [],
                        "res_norm0": nrmr0}
     s = psolve(A, r)
-    p = s  # the reference aliases p = s too (line 90); s is rebound, never mutated
+    # The reference aliases p = s (line 90) and later REBINDS p and r; here p and r are updated in
+    # place, so p needs storage of its own: psolve may return r itself (unpreconditioned CG) or the
+    # same pre-allocated vector on every call.
+    p = s.copy()
     cur = S_SR0
     dot_into(s, r, ctx.sptr(cur), ctx)
     _reduce(ctx, V, cur)

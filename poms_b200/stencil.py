@@ -61,6 +61,121 @@ class DeviceContext:
         return self.ws.data_ptr()
 
 
+class SubComm:
+    """The few mpi4py communicator methods the reference calls on `cart.subcomm[i]`
+    (sources/kron_product.py:156,224; pyccel/pyccel_functions.py:98,158): Allgatherv of host
+    arrays along one axis of the process grid.  Axis 1 = the slab group, other axes = one rank."""
+
+    def __init__(self, slab=None):
+        self.slab = slab if (slab is not None and slab.size > 1) else None
+
+    def Get_size(self):
+        return self.slab.size if self.slab is not None else 1
+
+    def Get_rank(self):
+        return self.slab.rank if self.slab is not None else 0
+
+    size = property(Get_size)
+    rank = property(Get_rank)
+
+    def py2f(self):
+        return 0
+
+    def Allgatherv(self, sendbuf, recvbuf):
+        """recvbuf: array, or [array, counts, displs(, type)] like mpi4py."""
+        send = np.ascontiguousarray(sendbuf, dtype=np.float64).reshape(-1)
+        if isinstance(recvbuf, (list, tuple)):
+            recv, counts, displs = recvbuf[0], recvbuf[1], recvbuf[2]
+        else:
+            recv, counts, displs = recvbuf, None, None
+        if self.slab is None:
+            recv.reshape(-1)[:send.size] = send
+            return
+        import torch.distributed as dist
+        G = self.slab.size
+        dev = self.slab.device if self.slab.device is not None else "cpu"
+        n = torch.tensor([send.size], dtype=torch.int64, device=dev)
+        ns = [torch.zeros_like(n) for _ in range(G)]
+        dist.all_gather(ns, n, group=self.slab.group)
+        ns = [int(v.item()) for v in ns]
+        mx = max(ns)
+        pad = torch.zeros(mx, dtype=torch.float64, device=dev)
+        pad[:send.size] = torch.as_tensor(send, device=dev)
+        parts = [torch.empty_like(pad) for _ in range(G)]
+        dist.all_gather(parts, pad, group=self.slab.group)
+        flat = recv.reshape(-1)
+        off = 0
+        for r in range(G):
+            o = int(displs[r]) if displs is not None else off
+            c = int(counts[r]) if counts is not None else ns[r]
+            flat[o:o + c] = parts[r][:c].cpu().numpy()
+            off += ns[r]
+
+
+class _PaddedData:
+    """`StencilVector._data` of spl: the local array padded by `pads` ghost entries on every side of
+    every axis (sources/utils.py:99, pyccel/kron_product.py:53,81-87 index it directly).  The device
+    storage has ghost planes along axis 1 only (slab partition) and none inside a plane, so this is a
+    host-side window: reads gather the padded array (in-plane ghosts of a non-periodic space are
+    zero), writes scatter the owned entries (and the axis-1 ghost planes that exist) back."""
+
+    def __init__(self, vec):
+        self._v = vec
+
+    @property
+    def shape(self):
+        V = self._v.space
+        return tuple(n + 2 * p for n, p in zip(V.local_shape, V.pads))
+
+    def _gather(self):
+        v = self._v
+        V = v.space
+        out = np.zeros(self.shape)
+        own = tuple(slice(p, p + n) for n, p in zip(V.local_shape, V.pads))
+        out[own] = v.data.cpu().numpy()
+        p0 = V.pads[0]
+        rest = own[1:]
+        if V.glo:
+            out[(slice(p0 - V.glo, p0),) + rest] = v._log[:V.glo].cpu().numpy()
+        if V.ghi:
+            n0 = V.local_shape[0]
+            out[(slice(p0 + n0, p0 + n0 + V.ghi),) + rest] = v._log[V.glo + n0:].cpu().numpy()
+        return out
+
+    def _scatter(self, arr):
+        v = self._v
+        V = v.space
+        own = tuple(slice(p, p + n) for n, p in zip(V.local_shape, V.pads))
+        v.data.copy_(torch.as_tensor(np.ascontiguousarray(arr[own]), device=V.device))
+        p0, n0 = V.pads[0], V.local_shape[0]
+        rest = own[1:]
+        if V.glo:
+            v._log[:V.glo].copy_(torch.as_tensor(np.ascontiguousarray(
+                arr[(slice(p0 - V.glo, p0),) + rest]), device=V.device))
+        if V.ghi:
+            v._log[V.glo + n0:].copy_(torch.as_tensor(np.ascontiguousarray(
+                arr[(slice(p0 + n0, p0 + n0 + V.ghi),) + rest]), device=V.device))
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._gather()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, key):
+        return self._gather()[key]
+
+    def __setitem__(self, key, value):
+        a = self._gather()
+        a[key] = value
+        self._scatter(a)
+
+    def copy(self, order="C"):
+        return np.array(self._gather(), order=order)
+
+    @property
+    def T(self):
+        return self._gather().T
+
+
 class Cart:
     """Minimal cartesian-decomposition record (spl.ddm.cart.Cart attribute names)."""
 
@@ -80,7 +195,10 @@ class Cart:
             s1, e1 = 0, self.npts[0] - 1
         self.starts = (s1,) + tuple(0 for _ in self.npts[1:])
         self.ends = (e1,) + tuple(n - 1 for n in self.npts[1:])
-        self.subcomm = [None] * self.ndim
+        # one sub-communicator per axis (spl: cart.subcomm[i]; used by the reference's per-line
+        # Allgatherv, sources/kron_product.py:140-141,156,162): the slab group along axis 1, a
+        # single-rank communicator along every other axis
+        self.subcomm = [SubComm(slab if d == 0 else None) for d in range(self.ndim)]
         self.comm_cart = comm
 
 
@@ -162,6 +280,7 @@ class StencilVector:
         self._buf = _buf
         self.flat = _buf[V.glo:V.glo + V.local_shape[0]]          # owned planes, pitched
         self.data = self.flat[..., :V.local_shape[-1]]             # logical (n1, .., n_last) view
+        self._log = _buf[..., :V.local_shape[-1]]                  # same incl. the ghost planes
 
     # ---- spl-compatible surface ---------------------------------------------------------
     @property
@@ -198,14 +317,27 @@ class StencilVector:
                 out.append(int(i) - off)
         return tuple(out)
 
+    # Indexing uses GLOBAL indices like spl (axis 1 reaches into the ghost planes of a slab) and goes
+    # through the logical view: the zero pad column of the pitched storage is never addressed, so
+    # `x[:, :] = 1.` cannot corrupt the BLAS-1 kernels that run over it.  Deviation from spl: a full
+    # slice covers the owned entries (+ axis-1 ghost planes), spl's also covers in-plane ghosts, which
+    # this storage does not have (`_data` emulates them).
     def __getitem__(self, key):
-        v = self._buf[self._local(key)]
+        v = self._log[self._local(key)]
         return v.item() if v.ndim == 0 else v.cpu().numpy()
 
     def __setitem__(self, key, value):
         if isinstance(value, np.ndarray):
             value = torch.as_tensor(value, dtype=torch.float64, device=self._buf.device)
-        self._buf[self._local(key)] = value
+        self._log[self._local(key)] = value
+
+    @property
+    def _data(self):
+        return _PaddedData(self)
+
+    @_data.setter
+    def _data(self, arr):
+        _PaddedData(self)._scatter(np.asarray(arr, dtype=np.float64))
 
     def copy(self):
         w = StencilVector(self._space, _buf=torch.empty_like(self._buf))
