@@ -86,8 +86,9 @@ int poms_kron_matvec_3d_ex(const double* x, double* y, const double* b,
 void poms_set_force_generic(int flag);
 /* A/B timing only: fix the axis-1 chunk (planes per CTA) of the 3-D mat-vec; 0 = automatic. */
 void poms_set_matvec3d_chunk(int chunk);
-/* Kernel variant of the TMA path: 1 = anti-phase pipeline (default), 0 = round-1 kernel (one stage at a
- * time); initial value from the environment variable POMS_B200_MV3_VARIANT.  A/B timing and tests. */
+/* Kernel variant of the TMA path: 1 = split-barrier kernel with TMA epilogue tiles and shared pair sums
+ * (default), 0 = round-1 kernel (one CTA barrier per plane); initial value from the environment variable
+ * POMS_B200_MV3_VARIANT.  A/B timing and tests. */
 void poms_set_matvec3d_variant(int variant);
 
 /*
@@ -207,6 +208,30 @@ int poms_prolong_3d(const double* coarse, double* fine, int n1f, int n2f, int n3
 
 /* y = Ainv x, dense row-major n x n (replicated coarse direct solve, sources/mg_jac.py:98-99) */
 int poms_dense_matvec(const double* Ainv, const double* x, double* y, int n, void* stream);
+
+/*
+ * Peer-memory halo exchange (one process per GPU, one box): replaces the MPI ghost update of spl's
+ * `update_ghost_regions` (sources/kron_product.py:76,87; sources/solvers.py:162,215) without NCCL.
+ * poms_ipc_*: thin wrappers of cudaMalloc / cudaIpc{Get,Open,Close}MemHandle so that the Python
+ * host side can map the vector arenas and flag words of the two slab neighbours (handles travel
+ * over torch.distributed); `handle` buffers hold poms_ipc_handle_bytes() bytes.
+ * poms_halo_exchange_p2p: ONE kernel that pushes `n_doubles` doubles (the outermost owned planes,
+ * contiguous because axis 1 is slowest) from src_lo / src_hi into the neighbours' ghost planes
+ * dst_lo / dst_hi (peer pointers) and handshakes through the flag words (poms_halo_flags_bytes()
+ * zero-initialised bytes per rank; lo_flags / hi_flags = the neighbours' words, NULL = no
+ * neighbour on that side).  Collective over the neighbours: every rank must launch the same
+ * sequence of exchanges.  Graph-capturable (the sequence number lives on the device).
+ */
+int poms_ipc_alloc(int64_t bytes, void** ptr_out);
+int poms_ipc_free(void* ptr);
+int poms_ipc_handle_bytes(void);
+int poms_ipc_get_handle(void* ptr, void* handle_out);
+int poms_ipc_open(const void* handle, void** ptr_out);
+int poms_ipc_close(void* ptr);
+int poms_halo_flags_bytes(void);
+int poms_halo_exchange_p2p(const double* src_lo, double* dst_lo, const double* src_hi, double* dst_hi,
+                           int64_t n_doubles, void* my_flags, void* lo_flags, void* hi_flags,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,14 @@ _PROTOS = {
                                   _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "poms_prolong_3d": (C.c_int, [_vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _l, _l,
                                  _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "poms_ipc_alloc": (C.c_int, [_l, C.POINTER(C.c_void_p)]),
+    "poms_ipc_free": (C.c_int, [_vp]),
+    "poms_ipc_handle_bytes": (C.c_int, []),
+    "poms_ipc_get_handle": (C.c_int, [_vp, C.c_char_p]),
+    "poms_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "poms_ipc_close": (C.c_int, [_vp]),
+    "poms_halo_flags_bytes": (C.c_int, []),
+    "poms_halo_exchange_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp]),
 }
 
 EXPORTS = tuple(_PROTOS)

@@ -1,0 +1,162 @@
+// poms_extra.cu -- self-contained units of libpoms_b200.so (own kernels + C ABI, see
+// include/poms_b200.h):
+//   * peer-memory halo exchange over NVLink (CUDA IPC): replaces the NCCL send/recv pair behind
+//     `update_ghost_regions` (/root/reference/sources/kron_product.py:76,87, solvers.py:162,215)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "poms_b200.h"
+
+#define POMS_HIDDEN __attribute__((visibility("hidden")))
+extern POMS_HIDDEN thread_local char g_err[256];
+extern POMS_HIDDEN int64_t g_launches;
+
+static int x_fail_cuda(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return (int)e;
+}
+static int x_bad_arg(int idx, const char* what) {
+    snprintf(g_err, sizeof(g_err), "bad argument %d: %s", idx, what);
+    return -idx;
+}
+
+// ------------------------------------------------------------------------------------------
+// CUDA IPC plumbing: one process per GPU; a rank maps the arenas of its two slab neighbours
+// ------------------------------------------------------------------------------------------
+extern "C" int poms_ipc_alloc(int64_t bytes, void** ptr_out) {
+    if (bytes <= 0) return x_bad_arg(1, "bytes");
+    if (!ptr_out) return x_bad_arg(2, "ptr_out");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e != cudaSuccess) return x_fail_cuda(e, "poms_ipc_alloc(cudaMalloc)");
+    e = cudaMemset(p, 0, (size_t)bytes);
+    if (e != cudaSuccess) return x_fail_cuda(e, "poms_ipc_alloc(cudaMemset)");
+    *ptr_out = p;
+    return 0;
+}
+extern "C" int poms_ipc_free(void* ptr) {
+    cudaError_t e = cudaFree(ptr);
+    return e == cudaSuccess ? 0 : x_fail_cuda(e, "poms_ipc_free");
+}
+extern "C" int poms_ipc_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+extern "C" int poms_ipc_get_handle(void* ptr, void* handle_out) {
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) return x_fail_cuda(e, "poms_ipc_get_handle");
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+extern "C" int poms_ipc_open(const void* handle, void** ptr_out) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return x_fail_cuda(e, "poms_ipc_open");
+    *ptr_out = p;
+    return 0;
+}
+extern "C" int poms_ipc_close(void* ptr) {
+    cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    return e == cudaSuccess ? 0 : x_fail_cuda(e, "poms_ipc_close");
+}
+
+// ------------------------------------------------------------------------------------------
+// Halo exchange by peer stores.  Every rank pushes its outermost `width` owned planes straight
+// into the ghost planes of its neighbours (NVLink peer writes), so there is no staging buffer,
+// no pack kernel and no NCCL proxy: ONE small kernel per exchange.
+//
+// flags (uint64, in the rank's own IPC-shared memory; neighbours write into them):
+//   [0] sequence number of the last completed exchange (own; lives on the device so that the
+//       kernel can be replayed from a CUDA graph)
+//   [1] / [2]  "entered exchange s" written by the lower / upper neighbour: everything queued
+//       before its exchange kernel has finished, so its ghost planes may be overwritten
+//   [3] / [4]  "data of exchange s has landed" written by the lower / upper neighbour
+//   [5] block ticket
+// Protocol of exchange s on every rank: signal ENTER to both neighbours; wait for their ENTER;
+// push; fence; the last block signals DATA and waits for the neighbours' DATA before it exits,
+// so the next kernel in the stream sees complete ghost planes.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void spin_until(const uint64_t* p, uint64_t seq) {
+    while (ld_acquire_sys(p) < seq) __nanosleep(20);
+}
+
+__global__ void __launch_bounds__(256) halo_push_kernel(
+    const double* __restrict__ src_lo, double* __restrict__ dst_lo,   // my lowest owned planes -> lower neighbour
+    const double* __restrict__ src_hi, double* __restrict__ dst_hi,   // my highest owned planes -> upper neighbour
+    int64_t n2, /* double2 elements per direction */
+    uint64_t* my_flags, uint64_t* lo_flags, uint64_t* hi_flags) {
+    __shared__ uint64_t s_seq;
+    if (threadIdx.x == 0) {
+        const uint64_t seq = ld_acquire_sys(my_flags + 0) + 1;
+        if (blockIdx.x == 0) {
+            if (lo_flags) st_release_sys(lo_flags + 2, seq);   // I am the lower rank's UPPER neighbour
+            if (hi_flags) st_release_sys(hi_flags + 1, seq);
+        }
+        if (lo_flags) spin_until(my_flags + 1, seq);
+        if (hi_flags) spin_until(my_flags + 2, seq);
+        s_seq = seq;
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lo_flags) {
+        const double2* s = reinterpret_cast<const double2*>(src_lo);
+        double2* d = reinterpret_cast<double2*>(dst_lo);
+        for (int64_t i = t0; i < n2; i += stride) d[i] = s[i];
+    }
+    if (hi_flags) {
+        const double2* s = reinterpret_cast<const double2*>(src_hi);
+        double2* d = reinterpret_cast<double2*>(dst_hi);
+        for (int64_t i = t0; i < n2; i += stride) d[i] = s[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint64_t seq = s_seq;
+        unsigned* ticket = reinterpret_cast<unsigned*>(my_flags + 5);
+        const unsigned t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {
+            __threadfence_system();
+            *ticket = 0u;
+            if (lo_flags) st_release_sys(lo_flags + 4, seq);
+            if (hi_flags) st_release_sys(hi_flags + 3, seq);
+            if (lo_flags) spin_until(my_flags + 3, seq);
+            if (hi_flags) spin_until(my_flags + 4, seq);
+            st_release_sys(my_flags + 0, seq);
+        }
+    }
+}
+
+extern "C" int poms_halo_flags_bytes(void) { return 64; }
+
+extern "C" int poms_halo_exchange_p2p(const double* src_lo, double* dst_lo, const double* src_hi, double* dst_hi,
+                                      int64_t n_doubles, void* my_flags, void* lo_flags, void* hi_flags,
+                                      void* stream) {
+    if (!my_flags) return x_bad_arg(6, "my_flags");
+    if (lo_flags && (!src_lo || !dst_lo)) return x_bad_arg(1, "lower neighbour pointers");
+    if (hi_flags && (!src_hi || !dst_hi)) return x_bad_arg(3, "upper neighbour pointers");
+    if (n_doubles < 0 || (n_doubles & 1)) return x_bad_arg(5, "n_doubles must be even (16-byte copies)");
+    if ((((uintptr_t)src_lo | (uintptr_t)dst_lo | (uintptr_t)src_hi | (uintptr_t)dst_hi) & 15) != 0)
+        return x_bad_arg(1, "halo blocks must be 16-byte aligned");
+    if (!lo_flags && !hi_flags) return 0;
+    const int64_t n2 = n_doubles / 2;
+    int blocks = (int)((n2 + 256 * 8 - 1) / (256 * 8));   // ~8 x 16 B per thread
+    if (blocks < 1) blocks = 1;
+    if (blocks > 96) blocks = 96;                          // all blocks resident at once on 148 SMs
+    halo_push_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src_lo, dst_lo, src_hi, dst_hi, n2,
+                                                              (uint64_t*)my_flags, (uint64_t*)lo_flags,
+                                                              (uint64_t*)hi_flags);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return x_fail_cuda(e, "poms_halo_exchange_p2p");
+    return 0;
+}

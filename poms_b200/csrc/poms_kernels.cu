@@ -18,14 +18,26 @@
 #define POMS_MAX_PARTIALS 65536
 #define POMS_WS_HEADER 256
 
-static thread_local char g_err[256] = "";
-static int64_t g_launches = 0;
+// The library is built from several translation units of THIS file (build.py: -DPOMS_TU=k) so that
+// the heavy template families compile in parallel: 0 = everything else, 1..5 = TMA 3-D mat-vec of
+// degree k, 6 = generic 3-D mat-vec.  Error text and launch counter live in TU 0.
+#ifndef POMS_TU
+#define POMS_TU 0
+#endif
+#define POMS_HIDDEN __attribute__((visibility("hidden")))
+#if POMS_TU == 0
+POMS_HIDDEN thread_local char g_err[256] = "";
+POMS_HIDDEN int64_t g_launches = 0;
+#else
+extern POMS_HIDDEN thread_local char g_err[256];
+extern POMS_HIDDEN int64_t g_launches;
+#endif
 
-static int fail_cuda(cudaError_t e, const char* where) {
+[[maybe_unused]] static int fail_cuda(cudaError_t e, const char* where) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
     return (int)e;
 }
-static int bad_arg(int idx, const char* what) {
+[[maybe_unused]] static int bad_arg(int idx, const char* what) {
     snprintf(g_err, sizeof(g_err), "bad argument %d: %s", idx, what);
     return -idx;
 }
@@ -36,6 +48,7 @@ static int bad_arg(int idx, const char* what) {
         if (e_ != cudaSuccess) return fail_cuda(e_, where);     \
     } while (0)
 
+#if POMS_TU == 0
 extern "C" int poms_version(void) { return 100; }
 extern "C" int64_t poms_workspace_bytes(void) {
     return POMS_WS_HEADER + (int64_t)POMS_MAX_PARTIALS * sizeof(double);
@@ -43,6 +56,7 @@ extern "C" int64_t poms_workspace_bytes(void) {
 extern "C" const char* poms_last_error(void) { return g_err; }
 extern "C" int64_t poms_launch_count(void) { return g_launches; }
 extern "C" void poms_launch_count_add(int64_t n) { g_launches += n; }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // cp.async helpers (Ampere-style asynchronous global -> shared copies, 8 bytes per thread)
@@ -165,6 +179,9 @@ struct MV3 {
     int chunk;  // output planes per CTA along axis 1
 };
 
+POMS_HIDDEN int poms_mv3_generic_launch(const MV3& a, int p, int form, int epi, dim3 grid, cudaStream_t st);
+
+#if POMS_TU == 6
 template <int P, int FORM, int EPI>
 __global__ void __launch_bounds__(256, 2) kron_matvec3d_kernel(MV3 a) {
     constexpr int W = 2 * P + 1;
@@ -363,7 +380,19 @@ static int launch_mv3(const MV3& a, int form, int epi, dim3 grid, cudaStream_t s
     if (form == POMS_FORM_SUM) return launch_mv3_epi<P, POMS_FORM_SUM>(a, epi, grid, st);
     return bad_arg(12, "form");
 }
+int poms_mv3_generic_launch(const MV3& a, int p, int form, int epi, dim3 grid, cudaStream_t st) {
+    switch (p) {
+        case 1: return launch_mv3<1>(a, form, epi, grid, st);
+        case 2: return launch_mv3<2>(a, form, epi, grid, st);
+        case 3: return launch_mv3<3>(a, form, epi, grid, st);
+        case 4: return launch_mv3<4>(a, form, epi, grid, st);
+        case 5: return launch_mv3<5>(a, form, epi, grid, st);
+        default: return bad_arg(11, "p must be 1..5");
+    }
+}
+#endif  // POMS_TU == 6
 
+#if POMS_TU == 0
 static int g_chunk_override = 0;   // > 0: fixed axis-1 chunk (A/B timing only)
 extern "C" void poms_set_matvec3d_chunk(int c) { g_chunk_override = c; }
 static int pick_chunk(int n1, int64_t tiles, int p) {
@@ -382,8 +411,11 @@ static int pick_chunk(int n1, int64_t tiles, int p) {
     if (chunk > n1) chunk = n1;
     return chunk;
 }
+#endif
 
 #include "poms_matvec3d_tma.cuh"
+
+#if POMS_TU == 0
 
 extern "C" int poms_kron_matvec_3d_ex(const double* x, double* y, const double* b, int n1, int n2,
                                       int n3, int64_t ld, int64_t pld, int glo, int ghi, int p,
@@ -442,15 +474,7 @@ extern "C" int poms_kron_matvec_3d_ex(const double* x, double* y, const double* 
     if ((int64_t)g3 * g2 * g1 > POMS_MAX_PARTIALS) return bad_arg(4, "grid too large for ws");
     dim3 grid(g3, g2, g1);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    switch (p) {
-        case 1: rc = launch_mv3<1>(a, form, epilogue, grid, st); break;
-        case 2: rc = launch_mv3<2>(a, form, epilogue, grid, st); break;
-        case 3: rc = launch_mv3<3>(a, form, epilogue, grid, st); break;
-        case 4: rc = launch_mv3<4>(a, form, epilogue, grid, st); break;
-        case 5: rc = launch_mv3<5>(a, form, epilogue, grid, st); break;
-        default: return bad_arg(11, "p must be 1..5");
-    }
+    const int rc = poms_mv3_generic_launch(a, p, form, epilogue, grid, st);
     if (rc) return rc;
     CHECK_LAUNCH("poms_kron_matvec_3d");
     return 0;
@@ -1608,3 +1632,4 @@ extern "C" int poms_dense_matvec(const double* Ainv, const double* x, double* y,
 }
 
 #include "poms_transfer3d.cuh"
+#endif  // POMS_TU == 0

@@ -69,6 +69,13 @@ struct MV3TCfg {
     }
 };
 
+POMS_HIDDEN int poms_mv3_tma_launch_p1(const CUtensorMap* tm3, const MV3T&, int form, int epi, int variant, int ntiles, dim3, cudaStream_t);
+POMS_HIDDEN int poms_mv3_tma_launch_p2(const CUtensorMap* tm3, const MV3T&, int form, int epi, int variant, int ntiles, dim3, cudaStream_t);
+POMS_HIDDEN int poms_mv3_tma_launch_p3(const CUtensorMap* tm3, const MV3T&, int form, int epi, int variant, int ntiles, dim3, cudaStream_t);
+POMS_HIDDEN int poms_mv3_tma_launch_p4(const CUtensorMap* tm3, const MV3T&, int form, int epi, int variant, int ntiles, dim3, cudaStream_t);
+POMS_HIDDEN int poms_mv3_tma_launch_p5(const CUtensorMap* tm3, const MV3T&, int form, int epi, int variant, int ntiles, dim3, cudaStream_t);
+
+#if POMS_TU >= 1 && POMS_TU <= 5
 #ifndef POMS_MV3_MINB
 #define POMS_MV3_MINB 2
 #endif
@@ -408,7 +415,61 @@ kron_matvec3d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
 }
 
 // ---- host side -----------------------------------------------------------------------------
-#include "poms_matvec3d_pipe.cuh"
+#include "poms_matvec3d_v3.cuh"
+
+// tm3: [0] halo'd input planes of x, [1] rhs tiles, [2] x tiles (variant 1 only; unused ones repeat [0])
+template <int P, int FORM, int EPI, int VAR>
+static int launch_mv3_tma_inst(const CUtensorMap* tm3, const MV3T& g, int ntiles, dim3 grid, cudaStream_t st) {
+    if (VAR == 0) {
+        const size_t smem = MV3TCfg<P>::smem_bytes(FORM == POMS_FORM_SUM);
+        auto kern = kron_matvec3d_tma_kernel<P, FORM, EPI>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(tma)");
+            attr_set = true;
+        }
+        kern<<<grid, 256, smem, st>>>(tm3[0], g);
+    } else {
+        auto kern = kron_matvec3d_v3_kernel<P, FORM, EPI>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            const size_t smax = MV3V3Cfg<P>::smem_bytes(FORM == POMS_FORM_SUM, 2);
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(v3)");
+            attr_set = true;
+        }
+        const size_t smem = MV3V3Cfg<P>::smem_bytes(FORM == POMS_FORM_SUM, ntiles);
+        kern<<<grid, 256, smem, st>>>(tm3[0], tm3[1], tm3[2], g);
+    }
+    return 0;
+}
+template <int P, int FORM, int VAR>
+static int launch_mv3_tma_epi(const CUtensorMap* tm3, const MV3T& g, int epi, int ntiles, dim3 grid, cudaStream_t st) {
+    switch (epi) {
+        case POMS_EPI_STORE: return launch_mv3_tma_inst<P, FORM, POMS_EPI_STORE, VAR>(tm3, g, ntiles, grid, st);
+        case POMS_EPI_RESID: return launch_mv3_tma_inst<P, FORM, POMS_EPI_RESID, VAR>(tm3, g, ntiles, grid, st);
+        case POMS_EPI_JACOBI: return launch_mv3_tma_inst<P, FORM, POMS_EPI_JACOBI, VAR>(tm3, g, ntiles, grid, st);
+        case POMS_EPI_DINV: return launch_mv3_tma_inst<P, FORM, POMS_EPI_DINV, VAR>(tm3, g, ntiles, grid, st);
+        case POMS_EPI_AXPY: return launch_mv3_tma_inst<P, FORM, POMS_EPI_AXPY, VAR>(tm3, g, ntiles, grid, st);
+        default: return bad_arg(19, "epilogue");
+    }
+}
+#define POMS_CAT_(a, b) a##b
+#define POMS_CAT(a, b) POMS_CAT_(a, b)
+int POMS_CAT(poms_mv3_tma_launch_p, POMS_TU)(const CUtensorMap* tm3, const MV3T& g, int form, int epi, int variant,
+                                             int ntiles, dim3 grid, cudaStream_t st) {
+    constexpr int P = POMS_TU;
+    if (variant == 0) {
+        if (form == POMS_FORM_SINGLE) return launch_mv3_tma_epi<P, POMS_FORM_SINGLE, 0>(tm3, g, epi, ntiles, grid, st);
+        return launch_mv3_tma_epi<P, POMS_FORM_SUM, 0>(tm3, g, epi, ntiles, grid, st);
+    }
+    if (form == POMS_FORM_SINGLE) return launch_mv3_tma_epi<P, POMS_FORM_SINGLE, 1>(tm3, g, epi, ntiles, grid, st);
+    return launch_mv3_tma_epi<P, POMS_FORM_SUM, 1>(tm3, g, epi, ntiles, grid, st);
+}
+#endif  // POMS_TU in 1..5
+
+#if POMS_TU == 0
 #include <unordered_map>
 #include <mutex>
 
@@ -468,7 +529,7 @@ static int get_tmap(PFN_encodeTiled enc, const double* base, int n3, int n2, int
     return 0;
 }
 
-// kernel variant: 1 = anti-phase pipeline (round 2, default), 0 = round-1 kernel (A/B timing, tests)
+// kernel variant: 1 = split-barrier kernel of poms_matvec3d_v3.cuh (round 2, default), 0 = round-1 kernel (A/B timing, tests)
 static int g_mv3_variant = -1;
 extern "C" void poms_set_matvec3d_variant(int v) { g_mv3_variant = v; }
 static int mv3_variant() {
@@ -477,40 +538,6 @@ static int mv3_variant() {
         g_mv3_variant = e ? atoi(e) : 1;
     }
     return g_mv3_variant;
-}
-
-template <int P, int FORM, int EPI, int VAR>
-static int launch_mv3_tma_inst(const CUtensorMap& tm, const MV3T& g, dim3 grid, cudaStream_t st) {
-    const size_t smem = MV3TCfg<P>::smem_bytes(FORM == POMS_FORM_SUM);
-    auto kern = VAR == 0 ? kron_matvec3d_tma_kernel<P, FORM, EPI> : kron_matvec3d_pipe_kernel<P, FORM, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(tma)");
-        attr_set = true;
-    }
-    kern<<<grid, 256, smem, st>>>(tm, g);
-    return 0;
-}
-template <int P, int FORM, int VAR>
-static int launch_mv3_tma_epi(const CUtensorMap& tm, const MV3T& g, int epi, dim3 grid, cudaStream_t st) {
-    switch (epi) {
-        case POMS_EPI_STORE: return launch_mv3_tma_inst<P, FORM, POMS_EPI_STORE, VAR>(tm, g, grid, st);
-        case POMS_EPI_RESID: return launch_mv3_tma_inst<P, FORM, POMS_EPI_RESID, VAR>(tm, g, grid, st);
-        case POMS_EPI_JACOBI: return launch_mv3_tma_inst<P, FORM, POMS_EPI_JACOBI, VAR>(tm, g, grid, st);
-        case POMS_EPI_DINV: return launch_mv3_tma_inst<P, FORM, POMS_EPI_DINV, VAR>(tm, g, grid, st);
-        case POMS_EPI_AXPY: return launch_mv3_tma_inst<P, FORM, POMS_EPI_AXPY, VAR>(tm, g, grid, st);
-        default: return bad_arg(19, "epilogue");
-    }
-}
-template <int P>
-static int launch_mv3_tma(const CUtensorMap& tm, const MV3T& g, int form, int epi, dim3 grid, cudaStream_t st) {
-    if (mv3_variant() == 0) {
-        if (form == POMS_FORM_SINGLE) return launch_mv3_tma_epi<P, POMS_FORM_SINGLE, 0>(tm, g, epi, grid, st);
-        return launch_mv3_tma_epi<P, POMS_FORM_SUM, 0>(tm, g, epi, grid, st);
-    }
-    if (form == POMS_FORM_SINGLE) return launch_mv3_tma_epi<P, POMS_FORM_SINGLE, 1>(tm, g, epi, grid, st);
-    return launch_mv3_tma_epi<P, POMS_FORM_SUM, 1>(tm, g, epi, grid, st);
 }
 
 // returns 0 on success, 1 if the TMA path does not apply (caller falls back to the generic kernel),
@@ -549,19 +576,47 @@ static int try_matvec3d_tma(const MV3& a0, int p, int form, int epilogue, const 
     g.a.chunk = pick_chunk(a0.n1, (int64_t)g3 * g2, p);
     const int g1 = (a0.n1 + g.a.chunk - 1) / g.a.chunk;
     if ((int64_t)g3 * g2 * g1 > POMS_MAX_PARTIALS) return 1;
-    CUtensorMap tm;
+    CUtensorMap tm3[3];
     if (get_tmap(enc, a0.x - (int64_t)a0.glo * a0.pld, a0.n3, a0.n2, a0.n1 + a0.glo + a0.ghi, a0.ld, a0.pld,
-                 64 + 2 * p + 2 * sh, 16 + 2 * p, &tm))
+                 64 + 2 * p + 2 * sh, 16 + 2 * p, &tm3[0]))
         return 1;
+    tm3[1] = tm3[0];
+    tm3[2] = tm3[0];
+    int var = mv3_variant();
+    int ntiles = 0;
+    if (var != 0) {
+        // variant 1 (poms_matvec3d_v3.cuh): the sum form shares the pair sums of the SYMMETRIC interior
+        // rows between its M and K passes; the epilogue operands arrive as TMA tiles (16-byte aligned)
+        bool sym = true;
+        if (form == POMS_FORM_SUM)
+            for (int k = 0; k < W; ++k)
+                sym = sym && g.t1m[k] == g.t1m[W - 1 - k] && g.t2m[k] == g.t2m[W - 1 - k] &&
+                      g.t3m[k] == g.t3m[W - 1 - k] && g.t2k[k] == g.t2k[W - 1 - k] && g.t3k[k] == g.t3k[W - 1 - k];
+        const bool need_b = epilogue != POMS_EPI_STORE && a0.b != nullptr;
+        const bool need_x = (epilogue == POMS_EPI_STORE && a0.dot_out) || epilogue == POMS_EPI_JACOBI;
+        if (!sym || (need_b && ((uintptr_t)a0.b & 15))) {
+            var = 0;
+        } else {
+            if (need_b) {
+                if (get_tmap(enc, a0.b, a0.n3, a0.n2, a0.n1, a0.ld, a0.pld, 64 + 2 * sh, 16, &tm3[1])) return 1;
+                ++ntiles;
+            }
+            if (need_x) {
+                if (get_tmap(enc, a0.x - (int64_t)a0.glo * a0.pld, a0.n3, a0.n2, a0.n1 + a0.glo + a0.ghi, a0.ld,
+                             a0.pld, 64 + 2 * sh, 16, &tm3[2]))
+                    return 1;
+                ++ntiles;
+            }
+        }
+    }
     dim3 grid(g3, g2, g1);
-    int rc;
     switch (p) {
-        case 1: rc = launch_mv3_tma<1>(tm, g, form, epilogue, grid, st); break;
-        case 2: rc = launch_mv3_tma<2>(tm, g, form, epilogue, grid, st); break;
-        case 3: rc = launch_mv3_tma<3>(tm, g, form, epilogue, grid, st); break;
-        case 4: rc = launch_mv3_tma<4>(tm, g, form, epilogue, grid, st); break;
-        case 5: rc = launch_mv3_tma<5>(tm, g, form, epilogue, grid, st); break;
+        case 1: return poms_mv3_tma_launch_p1(tm3, g, form, epilogue, var, ntiles, grid, st);
+        case 2: return poms_mv3_tma_launch_p2(tm3, g, form, epilogue, var, ntiles, grid, st);
+        case 3: return poms_mv3_tma_launch_p3(tm3, g, form, epilogue, var, ntiles, grid, st);
+        case 4: return poms_mv3_tma_launch_p4(tm3, g, form, epilogue, var, ntiles, grid, st);
+        case 5: return poms_mv3_tma_launch_p5(tm3, g, form, epilogue, var, ntiles, grid, st);
         default: return bad_arg(11, "p must be 1..5");
     }
-    return rc;
 }
+#endif  // POMS_TU == 0

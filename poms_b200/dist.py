@@ -33,6 +33,96 @@ def block_bounds(n, size, rank):
     return s, e
 
 
+class _DeviceBlob:
+    """A raw device allocation exposed through __cuda_array_interface__ so that torch can view it
+    (torch.as_tensor) without owning it."""
+
+    def __init__(self, ptr, n_doubles):
+        self.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8",
+                                         "data": (int(ptr), False), "version": 2}
+
+
+class PeerArena:
+    """IPC-shared device memory for the vectors whose ghost planes are exchanged: every rank
+    allocates the same sequence of equally sized blocks (sizes are computed from the LARGEST slab),
+    so a vector sits at the same (chunk, offset) on every rank and a rank can address its
+    neighbours' copy through the chunk's mapped base pointer.  Blocks are never freed: the arena
+    holds the persistent work vectors of a hierarchy (`Level.ws`).  Chunks are opened lazily
+    (collective: handles travel with all_gather_object)."""
+
+    ALIGN = 512
+
+    def __init__(self, slab):
+        import ctypes as C
+        from . import _lib
+        self.slab = slab
+        self.L = _lib.lib()
+        self.C = C
+        self.chunk_bytes = int(float(os.environ.get("POMS_B200_ARENA_CHUNK_GB", "8")) * (1 << 30))
+        self.max_bytes = int(float(os.environ.get("POMS_B200_ARENA_MAX_GB", "96")) * (1 << 30))
+        self.total = 0
+        self.chunks = []          # dicts: base, size, used, tensor, lo (peer base), hi (peer base)
+        self.ok = True
+        fl = self._new_chunk(4096)
+        self.flags = fl           # word 0.. : this rank's handshake flags
+        self.ok = fl is not None
+
+    def _new_chunk(self, nbytes):
+        C, L, slab = self.C, self.L, self.slab
+        ptr = C.c_void_p()
+        hb = L.poms_ipc_handle_bytes()
+        handle = C.create_string_buffer(hb)
+        good = L.poms_ipc_alloc(nbytes, C.byref(ptr)) == 0
+        good = good and L.poms_ipc_get_handle(ptr, handle) == 0
+        mine = handle.raw if good else None
+        allh = [None] * slab.size
+        dist.all_gather_object(allh, mine, group=slab.group)
+        ch = {"base": ptr.value if good else 0, "size": nbytes, "used": 0, "lo": 0, "hi": 0}
+        if all(h is not None for h in allh):
+            for side, r in (("lo", slab.rank - 1), ("hi", slab.rank + 1)):
+                if 0 <= r < slab.size:
+                    q = C.c_void_p()
+                    if L.poms_ipc_open(C.c_char_p(allh[r]), C.byref(q)) == 0:
+                        ch[side] = q.value
+                    else:
+                        good = False
+        else:
+            good = False
+        # the decision must be the same on every rank
+        flag = torch.tensor([1 if good else 0], device=slab.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=slab.group)
+        if int(flag.item()) == 0:
+            return None
+        ch["tensor"] = torch.as_tensor(_DeviceBlob(ch["base"], nbytes // 8), device=slab.device)
+        self.chunks.append(ch)
+        self.total += nbytes
+        return ch
+
+    def alloc(self, n_doubles):
+        """(chunk index, byte offset, 1-D float64 view) or None when the arena is exhausted/unusable.
+        COLLECTIVE when a new chunk is needed (same call sequence on every rank)."""
+        if not self.ok:
+            return None
+        nbytes = -(-8 * int(n_doubles) // self.ALIGN) * self.ALIGN
+        for i, ch in enumerate(self.chunks[1:], start=1):
+            if ch["size"] - ch["used"] >= nbytes:
+                break
+        else:
+            want = max(self.chunk_bytes, nbytes)
+            if self.total + want > self.max_bytes:
+                return None
+            ch = self._new_chunk(want)
+            if ch is None:
+                self.ok = False
+                return None
+            i = len(self.chunks) - 1
+        off = ch["used"]
+        ch["used"] += nbytes
+        view = ch["tensor"][off // 8: off // 8 + int(n_doubles)]
+        view.zero_()
+        return i, off, view
+
+
 class Slab:
     def __init__(self, group=None, device=None):
         self.group = group if group is not None else dist.group.WORLD
@@ -47,6 +137,33 @@ class Slab:
         self.overlap = (device is not None and torch.device(device).type == "cuda"
                         and os.environ.get("POMS_B200_OVERLAP") == "1")
         self._comm_stream = None
+        # POMS_B200_P2P=0 keeps every halo exchange on NCCL send/recv.  Default on CUDA: the
+        # persistent work vectors live in an IPC-shared arena and ghost planes move by peer stores
+        # (csrc/poms_extra.cu); vectors outside the arena still go through NCCL.
+        self.arena = None
+        self._want_p2p = (device is not None and torch.device(device).type == "cuda"
+                          and self.size > 1 and os.environ.get("POMS_B200_P2P", "1") != "0")
+
+    def get_arena(self):
+        """The rank's peer arena (created on first use; collective), or None."""
+        if self._want_p2p and self.arena is None:
+            a = PeerArena(self)
+            self._want_p2p = a.ok
+            self.arena = a if a.ok else None
+        return self.arena
+
+    def alloc_planes(self, n_planes_max, plane_shape):
+        """Storage for a vector with at most `n_planes_max` planes (ghosts included; the same number
+        on every rank) from the peer arena: (tensor view of that many planes, arena key) or None."""
+        a = self.get_arena()
+        if a is None:
+            return None
+        per = int(np.prod(plane_shape))
+        got = a.alloc(n_planes_max * per)
+        if got is None:
+            return None
+        i, off, view = got
+        return view.view((n_planes_max,) + tuple(plane_shape)), (i, off)
 
     # ---- partition ---------------------------------------------------------------------------
     def bounds(self, n, rank=None):
@@ -87,9 +204,59 @@ class Slab:
                 req.wait()
 
     def exchange(self, v):
-        """Halo exchange of a StencilVector (p planes per neighbour)."""
+        """Halo exchange of a StencilVector (p planes per neighbour): peer stores over NVLink when
+        the vector lives in the peer arena on every rank, NCCL send/recv otherwise."""
         V = v.space
+        if self.size > 1 and self._p2p_ready(v):
+            self._exchange_p2p(v)
+            return
         self.exchange_planes(v._buf, V.local_shape[0], V.glo, V.ghi, V.pads[0])
+
+    def _p2p_ready(self, v):
+        """Decided ONCE per vector, collectively (first exchange): every rank holds it at the same
+        arena position."""
+        st = v.__dict__.get("_p2p")
+        if st is None:
+            key = v.__dict__.get("_arena_key") if self.arena is not None else None
+            if key is None:
+                # arena blocks are handed out in the same order and size on every rank (SPMD), so a
+                # vector outside the arena here is outside it everywhere: NCCL, no handshake
+                v.__dict__["_p2p"] = False
+                return False
+            keys = [None] * self.size
+            dist.all_gather_object(keys, key, group=self.group)
+            st = v.__dict__["_p2p"] = bool(key is not None and all(k == key for k in keys))
+        return st
+
+    def _exchange_p2p(self, v):
+        from . import _lib
+        V = v.space
+        a = self.arena
+        w = V.pads[0]
+        n_own = V.local_shape[0]
+        per = int(np.prod(V.pitched_shape[1:]))              # doubles per plane
+        i, off = v._arena_key
+        ch, fl = a.chunks[i], a.chunks[0]
+        base = v._buf.data_ptr()
+        assert base == ch["base"] + off
+        n_glob = V.npts[0]
+        src_lo = dst_lo = src_hi = dst_hi = lo_f = hi_f = None
+        if self.rank > 0:
+            assert V.glo == w and n_own >= w
+            s_, e_ = block_bounds(n_glob, self.size, self.rank - 1)
+            glo_nb = w if self.rank - 1 > 0 else 0
+            src_lo = base + 8 * per * V.glo
+            dst_lo = ch["lo"] + off + 8 * per * (glo_nb + (e_ - s_ + 1))   # its upper ghost planes
+            lo_f = fl["lo"]
+        if self.rank < self.size - 1:
+            assert V.ghi == w and n_own >= w
+            src_hi = base + 8 * per * (V.glo + n_own - w)
+            dst_hi = ch["hi"] + off                                         # its lower ghost planes
+            hi_f = fl["hi"]
+        with profiling.region("halo_exchange", 2 * 8 * w * per):
+            _lib.check(a.L.poms_halo_exchange_p2p(src_lo, dst_lo, src_hi, dst_hi, w * per, fl["base"],
+                                                  lo_f, hi_f, torch.cuda.current_stream().cuda_stream),
+                       "poms_halo_exchange_p2p")
 
     def exchange_async(self, v):
         """The same exchange on the communication stream, ordered after the work already queued on

@@ -479,7 +479,7 @@ class Level:
         d = self.__dict__.setdefault("_ws", {})
         v = d.get(name)
         if v is None:
-            v = d[name] = StencilVector(self.V)
+            v = d[name] = StencilVector(self.V, peer=True)
         return v
 
 
@@ -695,30 +695,45 @@ def vcycle(h, l, b):
 
 
 def _graphs_wanted(h, b):
-    """CUDA graphs for the PCG iteration: one device, no per-kernel instrumentation, not disabled."""
+    """How the PCG iteration is driven: 'graph' = two CUDA graphs per iteration (one device, no
+    per-kernel instrumentation, not disabled by POMS_B200_GRAPH=0); 'persistent' = the same two
+    bodies launched eagerly on the hierarchy's persistent vectors (slab-partitioned runs: the
+    vectors then live in the peer arena and every halo exchange is a peer store); None = the
+    launch-by-launch driver of solvers.py."""
     import os
     V = b.space
-    return (os.environ.get("POMS_B200_GRAPH", "1") != "0" and not profiling.enabled()
-            and (V.slab is None or V.slab.size == 1) and V.compatible(h.levels[0].V)
-            and V.pads == h.levels[0].V.pads)
+    if not (V.compatible(h.levels[0].V) and V.pads == h.levels[0].V.pads):
+        return None
+    if V.slab is not None and V.slab.size > 1:
+        return "persistent"
+    if os.environ.get("POMS_B200_GRAPH", "1") != "0" and not profiling.enabled():
+        return "graph"
+    return None
 
 
 class _PcgGraphs:
-    """Persistent PCG state of one hierarchy (x, r, p, q on the fine level) and the two CUDA graphs of
+    """Persistent PCG state of one hierarchy (x, r, p, q on the fine level) and the two halves of
     an iteration of /root/reference/sources/solvers.py:101-124 with the V-cycle as psolve:
         G1: q = A p ; p.q ; x += alpha p ; r -= alpha q ; r.r          (lines 103-111)
         G2: s = V-cycle(r) ; s.r ; p = s + beta p ; sr_old = sr         (lines 117-124)
     The break test between them (line 113) reads one scalar on the host.  The launch sequence of a
-    hierarchy is fixed and alpha / beta already live on the device, so the ~60 (C5) to ~90 launches of
-    an iteration become two graph launches: the coarse levels stop being launch-latency bound."""
+    hierarchy is fixed and alpha / beta already live on the device, so on one device the ~60 (C5)
+    to ~90 launches of an iteration are captured as two CUDA graphs: the coarse levels stop being
+    launch-latency bound.  capture=False (slab-partitioned runs) launches the same bodies eagerly;
+    the scalars are then all-reduced in place on the device."""
 
-    def __init__(self, h):
+    def __init__(self, h, capture=True):
+        import weakref
         from .solvers import S_RR, S_PQ, S_SR0, S_SR1
         lv = h.levels[0]
-        self.h = h
+        self._h = weakref.ref(h)          # no reference cycle: the graphs die with the hierarchy
+        self.capture = capture
         self.x, self.r, self.p, self.q = (lv.ws(n) for n in ("pcg_x", "pcg_r", "pcg_p", "pcg_q"))
         self.ctx = DeviceContext.get(h.device)
         self.S_OLD, self.S_NEW = S_SR0, S_SR1
+        self.n_g1 = self.n_g2 = 0
+        if not capture:
+            return
         L = _lib.lib()
         # eager dry run: creates every work vector, tensor map and function attribute, then capture
         self.r.flat.fill_(1.0)
@@ -738,6 +753,10 @@ class _PcgGraphs:
         self.n_g1, self.n_g2 = n1 - n0, L.poms_launch_count() - n1
         self.pad_clean()
 
+    @property
+    def h(self):
+        return self._h()
+
     def pad_clean(self):
         for v in (self.x, self.r, self.p, self.q):
             V = v.space
@@ -745,39 +764,52 @@ class _PcgGraphs:
                 v._buf[..., V.local_shape[-1]:] = 0.0
 
     def _g1_body(self):
-        from .solvers import S_RR, S_PQ
+        from .solvers import S_RR, S_PQ, _reduce
         A, ctx, L = self.h.levels[0].A, self.ctx, _lib.lib()
+        V = self.x.space
         A.apply(self.p, self.q, EPI_STORE, dot_ptr=ctx.sptr(S_PQ))
-        _lib.check(L.poms_cg_update(self.x.ptr, self.r.ptr, self.p.ptr, self.q.ptr, self.x.n_owned,
-                                    ctx.sptr(self.S_OLD), ctx.sptr(S_PQ), ctx.sptr(S_RR), ctx.ws_ptr,
-                                    _stream()), "poms_cg_update")
+        _reduce(ctx, V, S_PQ)
+        with profiling.region("cg_update", 48 * self.x.n_owned):
+            _lib.check(L.poms_cg_update(self.x.ptr, self.r.ptr, self.p.ptr, self.q.ptr, self.x.n_owned,
+                                        ctx.sptr(self.S_OLD), ctx.sptr(S_PQ), ctx.sptr(S_RR), ctx.ws_ptr,
+                                        _stream()), "poms_cg_update")
+        _reduce(ctx, V, S_RR)
 
     def _g2_body(self):
         from .stencil import dot_into
+        from .solvers import _reduce
         ctx, L = self.ctx, _lib.lib()
+        V = self.x.space
         s = vcycle(self.h, 0, self.r)
-        dot_into(s, self.r, ctx.sptr(self.S_NEW), ctx)
-        _lib.check(L.poms_p_update(self.p.ptr, s.ptr, self.p.n_owned, ctx.sptr(self.S_NEW),
-                                   ctx.sptr(self.S_OLD), _stream()), "poms_p_update")
+        with profiling.region("dot", 16 * self.x.n_owned):
+            dot_into(s, self.r, ctx.sptr(self.S_NEW), ctx)
+        _reduce(ctx, V, self.S_NEW)
+        with profiling.region("p_update", 24 * self.x.n_owned):
+            _lib.check(L.poms_p_update(self.p.ptr, s.ptr, self.p.n_owned, ctx.sptr(self.S_NEW),
+                                       ctx.sptr(self.S_OLD), _stream()), "poms_p_update")
         ctx.scal[self.S_OLD:self.S_OLD + 1].copy_(ctx.scal[self.S_NEW:self.S_NEW + 1])
 
     def run_g1(self):
+        if not self.capture:
+            return self._g1_body()
         self.g1.replay()
         _lib.lib().poms_launch_count_add(self.n_g1)
 
     def run_g2(self):
+        if not self.capture:
+            return self._g2_body()
         self.g2.replay()
         _lib.lib().poms_launch_count_add(self.n_g2)
 
 
-def _pcg_graphed(h, b, x0, tol, maxiter, abs_thresh=None):
+def _pcg_graphed(h, b, x0, tol, maxiter, abs_thresh=None, capture=True):
     """`solvers._pcg_driver(relative=True)` on the persistent state of `_PcgGraphs` (same operations,
     same order, same device scalars; p = s is realised as p = s + beta*0)."""
-    from .solvers import S_RR
+    from .solvers import S_RR, _reduce
     from .stencil import dot_into
     g = h.__dict__.get("_pcg_graphs")
-    if g is None:
-        g = h._pcg_graphs = _PcgGraphs(h)
+    if g is None or g.capture != capture:
+        g = h._pcg_graphs = _PcgGraphs(h, capture=capture)
     ctx, A = g.ctx, h.levels[0].A
     x, r, p = g.x, g.r, g.p
     if x0 is None:
@@ -788,6 +820,7 @@ def _pcg_graphed(h, b, x0, tol, maxiter, abs_thresh=None):
         if x0 is not x:
             x.flat.copy_(x0.flat)
         A.apply(x, r, EPI_RESID, b=b, dot_ptr=ctx.sptr(S_RR))
+    _reduce(ctx, b.space, S_RR)
     nrmr0 = sqrt(float(ctx.scal[S_RR].item()))
     thresh = (tol * nrmr0) ** 2
     if abs_thresh is not None:
@@ -829,11 +862,12 @@ def mg_pcg(h, b, x0=None, tol=1e-10, maxiter=200, criterion="relative", verbose=
 
     if criterion == "reference":
         return solvers.pcg(A, psolve, b, x0=x0, tol=tol, maxiter=maxiter, verbose=verbose)
-    graphed = _graphs_wanted(h, b) and not verbose
+    mode = None if verbose else _graphs_wanted(h, b)
+    graphed = mode == "graph"
 
     def drive(x0_, tol_, maxiter_, title, abs_thresh=None):
-        if graphed:
-            return _pcg_graphed(h, b, x0_, tol_, maxiter_, abs_thresh=abs_thresh)
+        if mode is not None:
+            return _pcg_graphed(h, b, x0_, tol_, maxiter_, abs_thresh=abs_thresh, capture=graphed)
         return solvers._pcg_driver(A, psolve, b, x0_, tol_, maxiter_, verbose, title,
                                    relative=True, abs_thresh=abs_thresh)
 

@@ -260,11 +260,20 @@ class StencilVectorSpace:
 
 
 class StencilVector:
-    def __init__(self, V, _buf=None, zero=True):
+    def __init__(self, V, _buf=None, zero=True, peer=False):
         """zero=False: storage is left uninitialised except for the pad column and the ghost
-        planes (for vectors that a kernel overwrites completely; saves a full-size memset)."""
+        planes (for vectors that a kernel overwrites completely; saves a full-size memset).
+        peer=True (persistent work vectors of slab-partitioned spaces): storage from the slab's
+        IPC-shared arena, so that halo exchanges are peer stores; COLLECTIVE (every rank must
+        create its peer vectors in the same order)."""
         self._space = V
         shape = (V.glo + V.local_shape[0] + V.ghi,) + V.pitched_shape[1:]
+        if _buf is None and peer and V.slab is not None and V.slab.size > 1:
+            n_max = -(-V.npts[0] // V.slab.size) + 2 * V.pads[0]   # largest slab + both ghost blocks
+            got = V.slab.alloc_planes(n_max, V.pitched_shape[1:])
+            if got is not None:
+                _buf = got[0][:shape[0]]                            # zero-initialised by the arena
+                self._arena_key = got[1]
         if _buf is None:
             if zero:
                 _buf = torch.zeros(shape, dtype=torch.float64, device=V.device)

@@ -32,6 +32,24 @@ def check(name, cond, info=""):
     ok = ok and bool(flag.item())
 
 
+# peer-store halo exchange (IPC arena, csrc/poms_extra.cu) against NCCL send/recv on the same data,
+# several rounds (sequence numbers), two widths, 2-D and 3-D
+for shape, pads in (((40 * world + 1, 12, 18), (3, 3, 3)), ((24 * world, 50), (4, 2)), ((16 * world + 3, 9, 7), (1, 1, 1))):
+    V = StencilVectorSpace(list(shape), list(pads), [False] * len(shape), device=dev, slab=slab)
+    va, vb = StencilVector(V, peer=True), StencilVector(V)
+    same = True
+    for rnd in range(4):
+        g = torch.Generator(device=dev).manual_seed(100 * rnd + rank)
+        t = torch.randn(V.local_shape, generator=g, dtype=torch.float64, device=dev)
+        va.data.copy_(t)
+        vb.data.copy_(t)
+        slab.exchange(va)
+        slab.exchange(vb)
+        torch.cuda.synchronize()
+        same = same and bool(torch.equal(va._buf, vb._buf))
+    check("halo exchange peer-store == NCCL %s pads %s (p2p %s)" % (shape, pads, va.__dict__.get("_p2p")),
+          same and (va.__dict__.get("_p2p") is True or os.environ.get("POMS_B200_P2P") == "0"))
+
 for (p, N) in ((3, (32 * world, 16, 24)), (2, (64, 40)), (3, (64 * world, 32)), (3, (128 * world, 16, 16))):
     d = len(N)
     knots = [bs.make_open_knots(p, n + p) for n in N]
