@@ -210,6 +210,16 @@ int poms_prolong_3d(const double* coarse, double* fine, int n1f, int n2f, int n3
 int poms_dense_matvec(const double* Ainv, const double* x, double* y, int n, void* stream);
 
 /*
+ * Dense per-axis contraction out[o,i,c] = sum_j Q[i,j] in[o,j,c] on the fp64 tensor cores (DMMA):
+ * the 1-D eigenbasis contractions of the fast-diagonalisation coarse solve that replaces
+ * splu(csc_matrix(Ac)).solve(rc) (sources/mg_jac.py:98-99; dense Kronecker solve of
+ * sources/kron_product.py:93-117).  Same array view as poms_axis_gather; Q is n_out x n_in row-major.
+ */
+int poms_axis_dense_dmma(const double* in, double* out, const double* Q, int n_in, int n_out,
+                         int64_t n_outer, int64_t so_in, int64_t sa_in, int64_t so_out,
+                         int64_t sa_out, int64_t n_inner, void* stream);
+
+/*
  * Peer-memory halo exchange (one process per GPU, one box): replaces the MPI ghost update of spl's
  * `update_ghost_regions` (sources/kron_product.py:76,87; sources/solvers.py:162,215) without NCCL.
  * poms_ipc_*: thin wrappers of cudaMalloc / cudaIpc{Get,Open,Close}MemHandle so that the Python

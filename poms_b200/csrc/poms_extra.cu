@@ -160,3 +160,109 @@ extern "C" int poms_halo_exchange_p2p(const double* src_lo, double* dst_lo, cons
     if (e != cudaSuccess) return x_fail_cuda(e, "poms_halo_exchange_p2p");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Dense per-axis contraction on the fp64 tensor cores (DMMA, mma.sync m8n8k4):
+//     out[o, i, c] = sum_j Q[i, j] * in[o, j, c]        (Q dense n_out x n_in, row-major)
+// the 1-D eigenbasis contractions of the fast-diagonalisation solve that replaces
+// splu(csc_matrix(Ac)).solve(rc) (/root/reference/sources/mg_jac.py:98-99) and the dense
+// Kronecker solve of /root/reference/sources/kron_product.py:93-117.  A/B partner of
+// poms_axis_gather with W = n_in (scalar FMA, one coefficient load per FMA).
+// CTA = 4 warps, tile 32 (i) x 64 (c) with K chunks of 32 staged in shared memory; a warp owns
+// 8 rows x 64 columns = 8 accumulator fragments.  TRANS: the contraction runs along the
+// CONTIGUOUS axis (n_inner == 1): the "column" index is then the outer index o.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+template <bool TRANS>
+__global__ void __launch_bounds__(128) axis_dense_dmma_kernel(
+    const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ Q, int n_in, int n_out,
+    int64_t so_in, int64_t sa_in, int64_t so_out, int64_t sa_out, int64_t n_cols) {
+    constexpr int TM = 32, TN = 64, TK = 32, QP = TK + 4, XP = TN + 8;
+    __shared__ double Qs[TM][QP];     // Q[i0 + r][k0 + k]
+    __shared__ double Xs[TK][XP];     // X[k0 + k][c0 + c]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = blockIdx.y * TM;
+    const int64_t c0 = (int64_t)blockIdx.x * TN;
+    const int64_t o = TRANS ? 0 : blockIdx.z;
+    const double* inb = in + o * so_in;
+    double* outb = out + o * so_out;
+    double acc[8][2];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = 0.0;
+    for (int k0 = 0; k0 < n_in; k0 += TK) {
+        // stage Q tile (coalesced along k) and X tile
+        for (int e = tid; e < TM * TK; e += 128) {
+            const int r = e / TK, k = e - r * TK;
+            const int i = i0 + r, j = k0 + k;
+            Qs[r][k] = (i < n_out && j < n_in) ? __ldg(Q + (int64_t)i * n_in + j) : 0.0;
+        }
+        if (!TRANS) {
+            for (int e = tid; e < TK * TN; e += 128) {
+                const int k = e / TN, c = e - k * TN;
+                const int j = k0 + k;
+                const int64_t cc = c0 + c;
+                Xs[k][c] = (j < n_in && cc < n_cols) ? inb[(int64_t)j * sa_in + cc] : 0.0;
+            }
+        } else {
+            for (int e = tid; e < TK * TN; e += 128) {
+                const int c = e / TK, k = e - c * TK;      // k fastest: contiguous in memory
+                const int j = k0 + k;
+                const int64_t cc = c0 + c;
+                Xs[k][c] = (j < n_in && cc < n_cols) ? in[cc * so_in + j] : 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < TK; kk += 4) {
+            const double a = Qs[warp * 8 + (lane >> 2)][kk + (lane & 3)];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const double b = Xs[kk + (lane & 3)][t * 8 + (lane >> 2)];
+                dmma8x8x4(acc[t][0], acc[t][1], a, b);
+            }
+        }
+        __syncthreads();
+    }
+    const int i = i0 + warp * 8 + (lane >> 2);
+    if (i < n_out) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t cc = c0 + t * 8 + 2 * (lane & 3) + h;
+                if (cc < n_cols) {
+                    if (!TRANS) outb[(int64_t)i * sa_out + cc] = acc[t][h];
+                    else out[cc * so_out + i] = acc[t][h];
+                }
+            }
+        }
+    }
+}
+
+extern "C" int poms_axis_dense_dmma(const double* in, double* out, const double* Q, int n_in, int n_out,
+                                    int64_t n_outer, int64_t so_in, int64_t sa_in, int64_t so_out,
+                                    int64_t sa_out, int64_t n_inner, void* stream) {
+    if (!in || !out || !Q) return x_bad_arg(1, "null pointer");
+    if (n_in < 1 || n_out < 1 || n_outer < 1 || n_inner < 1) return x_bad_arg(4, "extent");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_inner == 1) {
+        // contraction along the contiguous axis: columns = the n_outer lines
+        if (sa_in != 1 || sa_out != 1) return x_bad_arg(8, "contiguous axis needs unit stride");
+        dim3 grid((unsigned)((n_outer + 63) / 64), (unsigned)((n_out + 31) / 32), 1);
+        axis_dense_dmma_kernel<true><<<grid, 128, 0, st>>>(in, out, Q, n_in, n_out, so_in, 1, so_out, 1, n_outer);
+    } else {
+        if (n_outer > 65535) return x_bad_arg(6, "n_outer");
+        dim3 grid((unsigned)((n_inner + 63) / 64), (unsigned)((n_out + 31) / 32), (unsigned)n_outer);
+        axis_dense_dmma_kernel<false><<<grid, 128, 0, st>>>(in, out, Q, n_in, n_out, so_in, sa_in, so_out,
+                                                           sa_out, n_inner);
+    }
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return x_fail_cuda(e, "poms_axis_dense_dmma");
+    return 0;
+}

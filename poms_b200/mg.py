@@ -40,8 +40,21 @@ def fine_knots(Tc, ts):
     return np.sort(np.concatenate([np.asarray(Tc, float), np.asarray(ts, float)]), kind="stable")
 
 
+def _dense_mode():
+    """How dense per-axis contractions (eigenbases of the coarse solve) are applied: 'dmma' = fp64
+    tensor-core kernel poms_axis_dense_dmma (default; measured against the gather kernel in
+    profiles/r02_ab_dense_dmma_vs_gather.txt), 'gather' = poms_axis_gather with W = n."""
+    import os
+    return os.environ.get("POMS_B200_DENSE", "dmma")
+
+
 def _gather(src_ptr, dst_ptr, start, coef, n_in, n_out, n_outer, so_in, sa_in, so_out, sa_out,
-            n_inner, accumulate):
+            n_inner, accumulate, dense=False):
+    if dense and not accumulate and _dense_mode() == "dmma":
+        _lib.check(_lib.lib().poms_axis_dense_dmma(
+            src_ptr, dst_ptr, coef.data_ptr(), n_in, n_out, n_outer, so_in, sa_in, so_out, sa_out,
+            n_inner, _stream()), "poms_axis_dense_dmma")
+        return
     _lib.check(_lib.lib().poms_axis_gather(
         src_ptr, dst_ptr, start.data_ptr(), coef.data_ptr(), coef.shape[1], n_in, n_out, n_outer,
         so_in, sa_in, so_out, sa_out, n_inner, int(accumulate), _stream()), "poms_axis_gather")
@@ -50,9 +63,10 @@ def _gather(src_ptr, dst_ptr, start, coef, n_in, n_out, n_outer, so_in, sa_in, s
 class _AxisOp:
     """Row-compressed sparse matrix applied along one axis of a contiguous d-dim array."""
 
-    def __init__(self, start, coef, n_in, device):
+    def __init__(self, start, coef, n_in, device, dense=False):
         self.n_out, self.W = coef.shape
         self.n_in = int(n_in)
+        self.dense = bool(dense) and self.W == self.n_in and not np.any(start)
         self._start_host = np.ascontiguousarray(start, dtype=np.int32)
         self.start = torch.as_tensor(self._start_host, device=device)
         self.coef = torch.as_tensor(np.ascontiguousarray(coef, dtype=np.float64), device=device)
@@ -80,7 +94,7 @@ class _AxisOp:
             so_in, so_out = shape_in[1] * ld_in, self.n_out * ld_in
             sa_in = sa_out = n_inner = ld_in
         _gather(src.data_ptr(), dst.data_ptr(), self.start, self.coef, self.n_in, self.n_out,
-                n_outer, so_in, sa_in, so_out, sa_out, n_inner, accumulate)
+                n_outer, so_in, sa_in, so_out, sa_out, n_inner, accumulate, dense=self.dense)
         return tuple(shape_out)
 
 
@@ -360,8 +374,8 @@ class CoarseSolver:
             lam.append(w)
             n = Q.shape[0]
             z = np.zeros(n, dtype=np.int32)
-            self.Q.append(_AxisOp(z, Q, n, device))
-            self.Qt.append(_AxisOp(z, np.ascontiguousarray(Q.T), n, device))
+            self.Q.append(_AxisOp(z, Q, n, device, dense=True))
+            self.Qt.append(_AxisOp(z, np.ascontiguousarray(Q.T), n, device, dense=True))
         D = 0.0
         for a in range(A.ndim):
             t = np.ones(())
@@ -743,6 +757,10 @@ class _PcgGraphs:
         self._g2_body()
         self._g1_body()
         torch.cuda.synchronize()
+        # collect dead reference cycles NOW: torch.cuda.graph does not, and a CUDA graph or tensor
+        # freed by the cyclic collector in the middle of a capture invalidates it
+        import gc
+        gc.collect()
         self.g1, self.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         n0 = L.poms_launch_count()
         with torch.cuda.graph(self.g1):
