@@ -24,6 +24,27 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
+// Axis-1 partial sums in SHIFT form: after input plane j, acc[e][m] is the partial sum of output plane
+// j - P + m.  Plane j adds c[W-1-m] * value to it; in place that reads acc[m+1] (the same output one
+// plane earlier) and writes acc[m], for ascending m, so the window slides without a rotation index,
+// without register moves and without the 7-way switch of rot_scatter: one straight-line block of
+// W (2W for the sum form) independent FMA chains per point.  The completed plane is acc[e][0].
+template <int W, int E, bool TWO>
+__device__ __forceinline__ void shift_scatter(double (&acc)[E][W], const double (&ta)[E], const double (&tb)[E],
+                                              const double (&c1k)[W], const double (&c1m)[W], double (&vout)[E]) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+#pragma unroll
+        for (int m = 0; m < W - 1; ++m) {
+            acc[e][m] = fma(c1k[W - 1 - m], ta[e], acc[e][m + 1]);
+            if (TWO) acc[e][m] = fma(c1m[W - 1 - m], tb[e], acc[e][m]);
+        }
+        acc[e][W - 1] = c1k[0] * ta[e];
+        if (TWO) acc[e][W - 1] = fma(c1m[0], tb[e], acc[e][W - 1]);
+        vout[e] = acc[e][0];
+    }
+}
+
 template <int P>
 struct MV3V3Cfg : MV3TCfg<P> {
     using B = MV3TCfg<P>;
@@ -306,11 +327,11 @@ kron_matvec3d_v3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         }
     };
 
-    // ring slot / phase of the plane stage 1 handles next, su/sv buffer counter, rotation slot,
-    // epilogue tile counter
+    // state of the march: ring slot of the plane stage 1 handles next (+ phase bits of the ring),
+    // su/sv buffer counter, epilogue tile slot (+ phase bits)
     int s1slot = 0;
-    unsigned rphase = 0;
-    int cnt = 0, u = 0, ecnt = 0;
+    unsigned rphase = 0, ephase = 0;
+    int cnt = 0, eslot = 0;
 
     if (jv0 < jv1) {
         stage1(0, 0u, 0);
@@ -318,6 +339,48 @@ kron_matvec3d_v3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         s1slot = (NST > 1) ? 1 : 0;
     }
 
+    // thread 0, once every warp is past stage 1 of plane j and past the epilogue of plane j-2:
+    // refill the ring slot of plane j with plane j+NST, the tile slot of output plane j-P-2 with j-P+1
+    auto refill = [&](const int j, const bool ring_ok, const bool tile_ok) {
+        if (tid == 0) {
+            if (ring_ok) {
+                const int sl = (s1slot == 0) ? NST - 1 : s1slot - 1;      // slot of plane j
+                mbar_expect_tx(rfull + sl, R2 * C3 * 8);
+                tma_load_3d(ring + (size_t)sl * STAGE_D, &tmap, i3_0 - P, i2_0 - P, j + NST + a.glo, rfull + sl);
+            }
+            if (tile_ok) {
+                const int ti = j - P + 1;                                  // output plane of the NEXT iteration
+                const int sl = (eslot + 1 == NES) ? 0 : eslot + 1;
+                mbar_expect_tx(efull + sl, etx);
+                if (need_b) tma_load_3d(eb + (size_t)sl * ETILE_D, &tmb, i3_0 - SH, i2_0, ti, efull + sl);
+                if (need_x) tma_load_3d(ex + (size_t)sl * ETILE_D, &tmx, i3_0 - SH, i2_0, ti + a.glo, efull + sl);
+            }
+        }
+    };
+
+    // epilogue of output plane i1 for one point
+    auto emit_point = [&](const int e, const double v, const double bv, const double xv, const double dg1,
+                          const double dg2) {
+        if (EPI == POMS_EPI_STORE) {
+            yp[(int64_t)e * a.ld] = v;
+            if (need_x) dsum = fma(xv, v, dsum);
+        } else if (EPI == POMS_EPI_RESID) {
+            const double rr = bv - v;
+            yp[(int64_t)e * a.ld] = rr;
+            dsum = fma(rr, rr, dsum);
+        } else if (EPI == POMS_EPI_AXPY) {
+            const double w_ = a.omega * v;
+            yp[(int64_t)e * a.ld] = need_b ? bv + w_ : w_;
+            dsum = fma(w_, w_, dsum);
+        } else {
+            const double dg = TWO ? dg1 * dA[e] + dg2 * dB[e] : dg1 * dA[e];
+            const double dr = a.omega * (bv - v) / dg;
+            yp[(int64_t)e * a.ld] = (EPI == POMS_EPI_JACOBI) ? xv + dr : dr;
+            dsum = fma(dr, dr, dsum);
+        }
+    };
+
+    // ---- general plane step (boundary / ragged tiles, first and last planes of a chunk) ----------
     auto plane = [&](const int j, auto steady_tag) {
         constexpr bool STEADY = decltype(steady_tag)::value;
         const bool have = STEADY ? true : (j < jv1);
@@ -329,36 +392,22 @@ kron_matvec3d_v3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         } else {
             __syncthreads();   // drain planes (end of the last chunk only): orders the tile slots
         }
-        // every warp is past stage 1 of plane j and past the epilogue of plane j-2:
-        // refill the ring slot of plane j and the tile slot of output plane j-P-2
-        if (tid == 0) {
-            if (have && (STEADY || j + NST < jv1)) {
-                const int sl = (s1slot + NST - 1) % NST;      // slot of plane j
-                mbar_expect_tx(rfull + sl, R2 * C3 * 8);
-                tma_load_3d(ring + (size_t)sl * STAGE_D, &tmap, i3_0 - P, i2_0 - P, j + NST + a.glo, rfull + sl);
-            }
-            const int ti = j - P + 1;                          // output plane of the NEXT iteration
-            if (need_t && (STEADY || (ti >= c_lo + NES - 1 && ti < c_hi))) {
-                const int sl = (ti - c_lo) % NES;
-                mbar_expect_tx(efull + sl, etx);
-                if (need_b) tma_load_3d(eb + (size_t)sl * ETILE_D, &tmb, i3_0 - SH, i2_0, ti, efull + sl);
-                if (need_x) tma_load_3d(ex + (size_t)sl * ETILE_D, &tmx, i3_0 - SH, i2_0, ti + a.glo, efull + sl);
-            }
-        }
+        const int i1 = j - P;
+        const bool emit = STEADY ? true : (i1 >= c_lo);
+        refill(j, have && (STEADY || j + NST < jv1),
+               need_t && (STEADY || (i1 + 1 >= c_lo + NES - 1 && i1 + 1 < c_hi)));
         if (have && wlive) stage2(cnt & 1, ta, tb);
         if (STEADY || j + 1 < jv1) {
             stage1(s1slot, (rphase >> s1slot) & 1u, (cnt + 1) & 1);
             rphase ^= (1u << s1slot);
             s1slot = (s1slot + 1 == NST) ? 0 : s1slot + 1;
         }
-        const int i1 = j - P;
-        const bool emit = STEADY ? true : (i1 >= c_lo);
         if (wlive) {
-            // ---- stage 3: rotating axis-1 partial sums ----
+            // ---- stage 3: sliding axis-1 partial sums ----
             const bool toep1 = STEADY ? true : (have && (j - P >= g.lo1) && (j + P < g.hi1));
             if (toep1) {
-                rot_scatter<W, E, TWO>(u, acc, ta, tb, *(const double(*)[W])(TWO ? g.t1k : g.t1m),
-                                       *(const double(*)[W]) g.t1m, vout);
+                shift_scatter<W, E, TWO>(acc, ta, tb, *(const double(*)[W])(TWO ? g.t1k : g.t1m),
+                                         *(const double(*)[W]) g.t1m, vout);
             } else {
                 double c1k[W], c1m[W];
 #pragma unroll
@@ -373,49 +422,151 @@ kron_matvec3d_v3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
                         c1m[k] = 0.0;
                     }
                 }
-                rot_scatter<W, E, TWO>(u, acc, ta, tb, c1k, c1m, vout);
+                shift_scatter<W, E, TWO>(acc, ta, tb, c1k, c1m, vout);
             }
         }
         // ---- epilogue: output plane i1 = j - P ----
         if (emit) {
-            const int sl = ecnt % NES;
-            if (need_t) mbar_wait(efull + sl, (ecnt / NES) & 1);
+            if (need_t) mbar_wait(efull + eslot, (ephase >> eslot) & 1u);
+            ephase ^= (1u << eslot);
             if (wlive) {
-                const double* const ebt = eb + (size_t)sl * ETILE_D + eslot0;
-                const double* const ext = ex + (size_t)sl * ETILE_D + eslot0;
+                const double* const ebt = eb + (size_t)eslot * ETILE_D + eslot0;
+                const double* const ext = ex + (size_t)eslot * ETILE_D + eslot0;
                 double dg1 = 0.0, dg2 = 0.0;
                 if (EPI == POMS_EPI_JACOBI || EPI == POMS_EPI_DINV) {
                     dg1 = TWO ? __ldg(a.k1 + (int64_t)i1 * W + P) : __ldg(a.m1 + (int64_t)i1 * W + P);
                     dg2 = TWO ? __ldg(a.m1 + (int64_t)i1 * W + P) : 0.0;
                 }
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    if (okmask & (1u << e)) {
-                        const double v = vout[e];
-                        if (EPI == POMS_EPI_STORE) {
-                            yp[(int64_t)e * a.ld] = v;
-                            if (need_x) dsum = fma(ext[e * EW], v, dsum);
-                        } else if (EPI == POMS_EPI_RESID) {
-                            const double rr = ebt[e * EW] - v;
-                            yp[(int64_t)e * a.ld] = rr;
-                            dsum = fma(rr, rr, dsum);
-                        } else if (EPI == POMS_EPI_AXPY) {
-                            const double w_ = a.omega * v;
-                            yp[(int64_t)e * a.ld] = need_b ? ebt[e * EW] + w_ : w_;
-                            dsum = fma(w_, w_, dsum);
-                        } else {
-                            const double dg = TWO ? dg1 * dA[e] + dg2 * dB[e] : dg1 * dA[e];
-                            const double dr = a.omega * (ebt[e * EW] - v) / dg;
-                            yp[(int64_t)e * a.ld] = (EPI == POMS_EPI_JACOBI) ? ext[e * EW] + dr : dr;
-                            dsum = fma(dr, dr, dsum);
-                        }
-                    }
-                }
+                for (int e = 0; e < E; ++e)
+                    if (okmask & (1u << e))
+                        emit_point(e, vout[e], need_b ? ebt[e * EW] : 0.0, need_x ? ext[e * EW] : 0.0, dg1, dg2);
             }
             yp += a.pld;
-            ++ecnt;
+            eslot = (eslot + 1 == NES) ? 0 : eslot + 1;
         }
-        u = (u + 1 == W) ? 0 : u + 1;
+        ++cnt;
+    };
+
+    // ---- fast plane step: steady range of an INTERIOR tile (every row and column of the halo'd tile
+    // is a Toeplitz row, every point is inside the domain).  Both waits first, then ONE straight-line
+    // block -- stage 2 and stage 3 of plane j with stage 1 of plane j+1 -- so that the compiler can
+    // overlap the shared-memory latency of one stage with the FMA chains of the others.
+    auto plane_fast = [&](const int j) {
+        const int buf = cnt & 1;
+        mbar_wait(sfull + buf, (cnt >> 1) & 1);
+        mbar_wait(rfull + s1slot, (rphase >> s1slot) & 1u);
+        refill(j, true, need_t);
+        double ta[E], tb[E], vout[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) tb[e] = 0.0;
+        {
+            const double* const up = su + buf * C::SU_DOUBLES + (ty * E) * T3 + tx;
+            const double* const vp = sv + buf * C::SU_DOUBLES + (ty * E) * T3 + tx;
+            double w[E + 2 * P];
+#pragma unroll
+            for (int r = 0; r < E + 2 * P; ++r) w[r] = up[r * T3];
+            if (TWO) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    ta[e] = g.t2m[P] * w[e + P];
+                    tb[e] = g.t2k[P] * w[e + P];
+#pragma unroll
+                    for (int k = 1; k <= P; ++k) {
+                        const double sk = w[e + P - k] + w[e + P + k];
+                        ta[e] = fma(g.t2m[P + k], sk, ta[e]);
+                        tb[e] = fma(g.t2k[P + k], sk, tb[e]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < E + 2 * P; ++r) w[r] = vp[r * T3];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    tb[e] = fma(g.t2m[P], w[e + P], tb[e]);
+#pragma unroll
+                    for (int k = 1; k <= P; ++k) {
+                        const double sk = w[e + P - k] + w[e + P + k];
+                        tb[e] = fma(g.t2m[P + k], sk, tb[e]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    ta[e] = g.t2m[0] * w[e];
+#pragma unroll
+                    for (int k = 1; k < W; ++k) ta[e] = fma(g.t2m[k], w[e + k], ta[e]);
+                }
+            }
+        }
+        shift_scatter<W, E, TWO>(acc, ta, tb, *(const double(*)[W])(TWO ? g.t1k : g.t1m),
+                                 *(const double(*)[W]) g.t1m, vout);
+        {
+            const double* const sx = ring + (size_t)s1slot * STAGE_D + 2 * lane;
+            double* const sub = su + (buf ^ 1) * C::SU_DOUBLES + 2 * lane;
+            double* const svb = sv + (buf ^ 1) * C::SU_DOUBLES + 2 * lane;
+            auto row1 = [&](const int r) {
+                double xr[NX];
+                const double2* src = reinterpret_cast<const double2*>(sx + r * C3);
+#pragma unroll
+                for (int q = 0; q < NX / 2; ++q) {
+                    const double2 v2 = src[q];
+                    xr[2 * q] = v2.x;
+                    xr[2 * q + 1] = v2.y;
+                }
+                double ua, ub, va = 0.0, vb = 0.0;
+                if (TWO) {
+                    ua = g.t3m[P] * xr[P];
+                    ub = g.t3m[P] * xr[P + 1];
+                    va = g.t3k[P] * xr[P];
+                    vb = g.t3k[P] * xr[P + 1];
+#pragma unroll
+                    for (int k = 1; k <= P; ++k) {
+                        const double sa = xr[P - k] + xr[P + k];
+                        const double sb = xr[P + 1 - k] + xr[P + 1 + k];
+                        ua = fma(g.t3m[P + k], sa, ua);
+                        va = fma(g.t3k[P + k], sa, va);
+                        ub = fma(g.t3m[P + k], sb, ub);
+                        vb = fma(g.t3k[P + k], sb, vb);
+                    }
+                } else {
+                    ua = g.t3m[0] * xr[0];
+                    ub = g.t3m[0] * xr[1];
+#pragma unroll
+                    for (int k = 1; k < W; ++k) {
+                        ua = fma(g.t3m[k], xr[k], ua);
+                        ub = fma(g.t3m[k], xr[k + 1], ub);
+                    }
+                }
+                *reinterpret_cast<double2*>(sub + r * T3) = make_double2(ua, ub);
+                if (TWO) *reinterpret_cast<double2*>(svb + r * T3) = make_double2(va, vb);
+            };
+            row1(wid);
+            row1(wid + 8);
+            if (wid + 16 < R2) row1(wid + 16);
+            if (R2 > 24 && wid + 24 < R2) row1(wid + 24);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sfull + (buf ^ 1));
+        rphase ^= (1u << s1slot);
+        s1slot = (s1slot + 1 == NST) ? 0 : s1slot + 1;
+        // ---- epilogue ----
+        if (need_t) mbar_wait(efull + eslot, (ephase >> eslot) & 1u);
+        ephase ^= (1u << eslot);
+        {
+            const double* const ebt = eb + (size_t)eslot * ETILE_D + eslot0;
+            const double* const ext = ex + (size_t)eslot * ETILE_D + eslot0;
+            double dg1 = 0.0, dg2 = 0.0;
+            if (EPI == POMS_EPI_JACOBI || EPI == POMS_EPI_DINV) {
+                const int i1 = j - P;
+                dg1 = TWO ? __ldg(a.k1 + (int64_t)i1 * W + P) : __ldg(a.m1 + (int64_t)i1 * W + P);
+                dg2 = TWO ? __ldg(a.m1 + (int64_t)i1 * W + P) : 0.0;
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                emit_point(e, vout[e], need_b ? ebt[e * EW] : 0.0, need_x ? ext[e * EW] : 0.0, dg1, dg2);
+        }
+        yp += a.pld;
+        eslot = (eslot + 1 == NES) ? 0 : eslot + 1;
         ++cnt;
     };
 
@@ -425,11 +576,19 @@ kron_matvec3d_v3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
     s_lo = max(s_lo, c_lo + NES - 2 + P);
     int s_hi = min(jv1 - NST, min(c_hi + P - 1, g.hi1 - P));
     if (s_hi < s_lo) s_hi = s_lo = jv0;
+    // interior tile: no boundary rows / columns, no ragged edge
+    const bool cta_fast = toep2_cta && nb == 0 && qb == T3 / 2 && r_hi == R2 && i3_0 >= 0 &&
+                          i3_0 + T3 <= a.n3 && i2_0 + T2 <= a.n2;
     int j = jv0;
 #pragma unroll 1
     for (; j < s_lo; ++j) plane(j, std::false_type{});
+    if (cta_fast) {
 #pragma unroll 1
-    for (; j < s_hi; ++j) plane(j, std::true_type{});
+        for (; j < s_hi; ++j) plane_fast(j);
+    } else {
+#pragma unroll 1
+        for (; j < s_hi; ++j) plane(j, std::true_type{});
+    }
 #pragma unroll 1
     for (; j < jend; ++j) plane(j, std::false_type{});
     if (a.dot_out) {
