@@ -96,6 +96,18 @@ class ClockSampler:
 _cpu_port = {}
 
 
+def pin_cpu_threads():
+    """The CPU port parallelises with numba prange; BLAS/OpenMP pools underneath it oversubscribe the
+    cores (round 1: 2.7x run-to-run spread, the torchrun arm -- which exports OMP_NUM_THREADS=1 -- being
+    the fast one).  Pin: numba = all host cores, every BLAS/OpenMP pool = 1 thread.  Must run before
+    numba / numpy are imported."""
+    n = os.cpu_count() or 1
+    os.environ["NUMBA_NUM_THREADS"] = str(n)
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    return n
+
+
 def cpu_port_solve(ndim, p, N, tol=1e-10, smoother="glt", Nc=8):
     """One MG-PCG solve with the CPU port of the same algorithm: oracle/poms_oracle_mt.py (numba,
     all host threads), or the single-threaded NumPy oracle if numba is unavailable.  b = A x0 like
@@ -159,10 +171,20 @@ def _emit(line):
     _JSON_OUT.flush()
 
 
+REFERENCE_TIME_BUDGET_S = 240.0
+# Tier-A baseline: the UNMODIFIED reference timed in the dev container, one core
+# (it cannot travel: /root/reference does not exist on the GPU box) -- oracle/time_reference_c1.py
+TIER_A_NOTE = ("unmodified reference on C1 (2-D p=3 64x64, 4489 DOF), 1 core, dev container: see "
+               "profiles/r02_reference_tierA_c1.txt (oracle/time_reference_c1.py)")
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU algorithm on the host cores (oracle port)."""
+    """--impl reference: the reference's CPU algorithm on the host cores (oracle port).  Every step is
+    one full solve of the bounded sample; the run stops after REFERENCE_TIME_BUDGET_S seconds of
+    solves (reported: `steps` = solves actually timed, `steps_requested`, `time_budget_s`)."""
     if rank != 0:
         return
+    pin_cpu_threads()
     ndim, p, N, desc = CONFIGS[args.config]
     Ns = min(N, cpu_sample_size(ndim))
     vals = []
@@ -172,20 +194,26 @@ def run_reference(args, rank):
                                                      smoother=resolve_smoother(args.smoother, p))
         if i >= args.warmup:
             vals.append(dof / dt)
-        if time.perf_counter() - t_all > 200 and vals:
+        if time.perf_counter() - t_all > REFERENCE_TIME_BUDGET_S and i >= min(args.warmup, 1):
+            if not vals:
+                vals.append(dof / dt)
             break
     v = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "DOF/s", "n_gpus": args.gpus,
-        "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * dof / v,
+        "steps": len(vals), "steps_requested": args.steps, "time_budget_s": REFERENCE_TIME_BUDGET_S,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dof / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "%s (CPU sample: %d^%d elements, same MG-PCG algorithm, b = A x0)"
                                % (desc, Ns, ndim), "p": p, "ndim": ndim, "elements_per_axis": Ns,
                    "iterations": info["niter"]},
         "cpu_baseline": {"value": v, "unit": "DOF/s", "cores": cores, "kind": "port",
+                         "threads": {k: os.environ.get(k) for k in
+                                     ("NUMBA_NUM_THREADS", "OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS")},
                          "sample": "%d^%d elements, %s, %s smoother, full MG-PCG solve to 1e-10"
-                                   % (Ns, ndim, label, resolve_smoother(args.smoother, p))},
+                                   % (Ns, ndim, label, resolve_smoother(args.smoother, p)),
+                         "literal_reference_c1": TIER_A_NOTE},
         "e2e": {"value": v, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     _emit(line)
@@ -204,7 +232,10 @@ def main():
     ap.add_argument("--rhs", default="auto", choices=["auto", "ones", "manufactured"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--no-exact-glt", action="store_true",
+                    help="skip the extra solves with the reference's exact GLT smoother (N=1 only)")
     args = ap.parse_args()
+    pin_cpu_threads()
     _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -241,12 +272,15 @@ def main():
     lengths = [float(world)] + [1.0] * (ndim - 1)
     # coarsest level: solved exactly by fast diagonalisation, so it need not be tiny; stopping at 32
     # elements per axis in 3-D saves two levels of launch-latency-bound kernels per V-cycle
-    # With slabs the coarsest level must be small enough to be replicated (< 32 planes per rank), hence
-    # 16.  Levels are coarsened uniformly (all axes together): the elongated weak-scaling domain then
-    # has the same element shapes and the same number of levels as the single-GPU cube.
-    Nc = args.nc if args.nc > 0 else ((32 if world == 1 else 16) if ndim == 3 else 8)
+    # The same coarsest grid at every GPU count (32 elements per axis per GPU in 3-D): with slabs the
+    # coarsest level is gathered and solved redundantly; its 1-D eigenbasis along the slab axis is
+    # (32 G + p)^2 and is applied by the DMMA contraction kernel, so it stays cheap at 8 GPUs.
+    Nc = args.nc if args.nc > 0 else (32 if ndim == 3 else 8)
+    t_setup = time.perf_counter()
     h = Hierarchy(p, Ns, device=dev, smoother=args.smoother, nu=args.nu, slab=slab,
                   lengths=lengths, Nc=Nc, coarsen="uniform")
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
     V = h.levels[0].V
     dof_global = int(np.prod(V.npts))
     b = StencilVector(V)
@@ -353,6 +387,29 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = float(t.item())
 
+    # ---- the reference's own smoother beside the headline: glt_poly (polynomial approximation of the
+    # GLT solve, an EXTENSION) is the default for p <= 3; the exact GLT Kronecker solve
+    # (sources/solvers.py:260,288: kron_solve_par(M2, M1, r)) is timed on the same problem
+    exact_glt = None
+    if args.smoother == "glt_poly" and world == 1 and not args.no_exact_glt:
+        try:
+            hg = Hierarchy(p, Ns, device=dev, smoother="glt", nu=args.nu, slab=slab, lengths=lengths,
+                           Nc=Nc, coarsen="uniform")
+            xg, infog = mg_pcg(hg, b, tol=1e-10, maxiter=200)
+            barrier()
+            ng = min(args.steps, 3)
+            e0.record()
+            for _ in range(ng):
+                xg, infog = mg_pcg(hg, b, tol=1e-10, maxiter=200)
+            e1.record()
+            barrier()
+            exact_glt = {"smoother": "glt (exact banded Kronecker solves, the reference's post-smoother)",
+                         "ms_per_step": e0.elapsed_time(e1) / ng, "iterations": infog["niter"],
+                         "value": dof_global / (e0.elapsed_time(e1) / ng * 1e-3), "unit": "DOF/s"}
+            del hg, xg
+        except Exception as exc:                 # informational: never loses the headline
+            exact_glt = {"failed": repr(exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -371,15 +428,20 @@ def main():
         k = kern[dominant]
         avg_ms = k["ms"] / k["launches"]
         achieved = k["bytes"] / k["launches"] / (avg_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM traffic per launch: the per-variant ncu table (profiles/traffic.json: dram bytes read +
+        # written of one fine-level launch of every variant the solve uses) weighted by the variants'
+        # launch counts in one PCG iteration; null when no capture of this kernel family exists
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f).get(dominant)
             if tj:
                 traffic = tj["traffic_over_algorithmic"] * k["bytes"] / k["launches"]
+                traffic_src = tj.get("source")
         roof = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "launches": k["launches"],
                 "avg_launch_ms": avg_ms, "share_of_step": k["share"],
                 "algorithmic_bytes_per_launch": k["bytes"] / k["launches"]}
@@ -401,6 +463,13 @@ def main():
                    "ndim": ndim, "p": p, "elements": Ns, "dof": dof_global, "domain": lengths,
                    "solver": "pcg + V(%d,%d) %s-Chebyshev multigrid, tol 1e-10 relative"
                              % (args.nu, args.nu, args.smoother),
+                   "smoother_note": ("glt_poly = degree-3 polynomial approximation of the reference's GLT "
+                                     "Kronecker solve, an EXTENSION (DESIGN.md section 3); `exact_glt` "
+                                     "carries the same solve with the reference's exact GLT smoother")
+                                    if args.smoother == "glt_poly" else "reference smoother family",
+                   "setup_seconds": round(t_setup, 3),
+                   "setup_note": "Hierarchy construction (1-D operators, transfers, smoother bounds, "
+                                 "coarse eigenbases), outside the timed region",
                    "rhs": "b = 1 (mg_jac.py:59-61)" if rhs == "ones" else
                           "b = A x0, x0[i] = sum(i_a) + 1 (tests/test_pcg.py:52-58)",
                    "coarsest_elements": Nc,
@@ -415,6 +484,7 @@ def main():
                 "ms_per_step": ms_e2e, "h2d_bytes_per_step": 8 * nloc * world,
                 "d2h_bytes_per_step": 8 * nloc * world},
         "clocks": clocks,
+        "exact_glt": exact_glt,
         "roofline": roof,
         "kernels": {k: {"launches": v["launches"], "ms_per_step": round(v["ms_per_step"], 4),
                         "share": round(v["share"], 4), "gbs": round(v["gbs"], 1)}
@@ -433,6 +503,9 @@ def main():
             line["cpu_baseline"] = {
                 "value": dofc / dtc, "unit": "DOF/s", "cores": cores, "kind": "port",
                 "host_cores_available": os.cpu_count(),
+                "threads": {k: os.environ.get(k) for k in
+                            ("NUMBA_NUM_THREADS", "OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS")},
+                "literal_reference_c1": TIER_A_NOTE,
                 "sample": "%d^%d elements (%d DOF), one full MG-PCG solve to 1e-10, %s, %s smoother, "
                           "%d iterations, %.1f s" % (Ns_cpu, ndim, dofc, label, smo, infoc["niter"], dtc)}
         except Exception as exc:             # the GPU numbers above must still be reported

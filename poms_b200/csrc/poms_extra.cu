@@ -108,16 +108,22 @@ __global__ void __launch_bounds__(256) halo_push_kernel(
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (lo_flags) {
-        const double2* s = reinterpret_cast<const double2*>(src_lo);
-        double2* d = reinterpret_cast<double2*>(dst_lo);
-        for (int64_t i = t0; i < n2; i += stride) d[i] = s[i];
-    }
-    if (hi_flags) {
-        const double2* s = reinterpret_cast<const double2*>(src_hi);
-        double2* d = reinterpret_cast<double2*>(dst_hi);
-        for (int64_t i = t0; i < n2; i += stride) d[i] = s[i];
-    }
+    // four 16-byte loads in flight per thread before the peer stores (NVLink writes are posted)
+    auto push = [&](const double* src, double* dst) {
+        const double2* s = reinterpret_cast<const double2*>(src);
+        double2* d = reinterpret_cast<double2*>(dst);
+        int64_t i = t0;
+        for (; i + 3 * stride < n2; i += 4 * stride) {
+            const double2 a0 = s[i], a1 = s[i + stride], a2 = s[i + 2 * stride], a3 = s[i + 3 * stride];
+            d[i] = a0;
+            d[i + stride] = a1;
+            d[i + 2 * stride] = a2;
+            d[i + 3 * stride] = a3;
+        }
+        for (; i < n2; i += stride) d[i] = s[i];
+    };
+    if (lo_flags) push(src_lo, dst_lo);
+    if (hi_flags) push(src_hi, dst_hi);
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -151,7 +157,7 @@ extern "C" int poms_halo_exchange_p2p(const double* src_lo, double* dst_lo, cons
     const int64_t n2 = n_doubles / 2;
     int blocks = (int)((n2 + 256 * 8 - 1) / (256 * 8));   // ~8 x 16 B per thread
     if (blocks < 1) blocks = 1;
-    if (blocks > 96) blocks = 96;                          // all blocks resident at once on 148 SMs
+    if (blocks > 132) blocks = 132;                        // all blocks resident at once on 148 SMs
     halo_push_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src_lo, dst_lo, src_hi, dst_hi, n2,
                                                               (uint64_t*)my_flags, (uint64_t*)lo_flags,
                                                               (uint64_t*)hi_flags);

@@ -498,8 +498,13 @@ kron_matvec3d_v3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
                 }
             }
         }
+#ifndef POMS_V3_S3_SHADOW
+#define POMS_V3_S3_SHADOW 0
+#endif
+#if !POMS_V3_S3_SHADOW
         shift_scatter<W, E, TWO>(acc, ta, tb, *(const double(*)[W])(TWO ? g.t1k : g.t1m),
                                  *(const double(*)[W]) g.t1m, vout);
+#endif
         {
             const double* const sx = ring + (size_t)s1slot * STAGE_D + 2 * lane;
             double* const sub = su + (buf ^ 1) * C::SU_DOUBLES + 2 * lane;
@@ -549,6 +554,11 @@ kron_matvec3d_v3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         if (lane == 0) mbar_arrive(sfull + (buf ^ 1));
         rphase ^= (1u << s1slot);
         s1slot = (s1slot + 1 == NST) ? 0 : s1slot + 1;
+#if POMS_V3_S3_SHADOW
+        // experiment: axis-1 sums in the shadow between this warp's arrival and its next wait
+        shift_scatter<W, E, TWO>(acc, ta, tb, *(const double(*)[W])(TWO ? g.t1k : g.t1m),
+                                 *(const double(*)[W]) g.t1m, vout);
+#endif
         // ---- epilogue ----
         if (need_t) mbar_wait(efull + eslot, (ephase >> eslot) & 1u);
         ephase ^= (1u << eslot);
