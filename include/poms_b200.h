@@ -68,6 +68,17 @@ int poms_kron_matvec_3d(const double* x, double* y, const double* b,
                         const double* m3, const double* k3,
                         int epilogue, double omega, double* dot_out, void* ws, void* stream);
 
+/* poms_kron_matvec_2d plus HOST-side hints for the TMA kernel: toep_host[axis(0,1)][m,k][2p+1] = the
+ * interior (Toeplitz) band rows, toep_rng_host = {lo1, hi1, lo2, hi2} (rows [lo, hi) equal them bit for
+ * bit); NULL = no hint (every coefficient from global memory).  poms_set_matvec2d_variant(0) selects the
+ * round-1 kernel (A/B timing, tests); initial value from POMS_B200_MV2_VARIANT. */
+int poms_kron_matvec_2d_ex(const double* x, double* y, const double* b,
+                           int n1, int n2, int64_t ld, int glo, int ghi, int p, int form,
+                           const double* m1, const double* k1, const double* m2, const double* k2,
+                           int epilogue, double omega, double* dot_out, void* ws, void* stream,
+                           const double* toep_host, const int* toep_rng_host);
+void poms_set_matvec2d_variant(int variant);
+
 /*
  * Same as poms_kron_matvec_3d plus HOST-side hints that unlock the constant-bank coefficient path
  * of the TMA kernel: toep_host[axis(0,1,2)][m,k][2p+1] = the interior (Toeplitz) band row of the
@@ -99,6 +110,19 @@ void poms_set_matvec3d_variant(int variant);
 int poms_stencil_matvec_2d(const double* x, double* y, const double* b, const double* S,
                            int n1, int n2, int64_t ld, int glo, int ghi, int p1, int p2,
                            int epilogue, double omega, double* dot_out, void* ws, void* stream);
+
+/* The same in 3-D: S is (n1, n2, n3, 2p1+1, 2p2+1, 2p3+1) row-major ((2p+1)^3 coefficients per row: the
+ * kernel streams coefficients, one warp per output point).  EXTENSION to 3-D of the operator type the
+ * reference's solvers take (sources/solvers.py:85,103,209). */
+int poms_stencil_matvec_3d(const double* x, double* y, const double* b, const double* S,
+                           int n1, int n2, int n3, int64_t ld, int64_t pld, int glo, int ghi,
+                           int p1, int p2, int p3, int epilogue, double omega, double* dot_out,
+                           void* ws, void* stream);
+/* x[i] += d[i] on the points with (i1 + i2 + i3 + off) % 2 == colour (n1 = 1 for 2-D arrays): the half
+ * sweep of a two-colour (red-black) damped Jacobi smoother, named as future work in the reference's talk
+ * (slides/content.tex:393).  EXTENSION. */
+int poms_color_add(double* x, const double* d, int n1, int n2, int n3, int64_t ld, int64_t pld,
+                   int off, int colour, void* stream);
 
 /*
  * BLAS-1 pieces of the CG drivers over a flat range of `n` doubles (the owned planes are

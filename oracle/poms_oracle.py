@@ -716,3 +716,113 @@ class MGHierarchy:
             info["restarts"] += 1
         info["success"] = bool(info["res_norm"] ** 2 <= target)
         return x, info
+
+
+# ==========================================================================================
+# EXTENSION checkers: the solvers the reference names as future work (slides/content.tex:393-394)
+# and the full 3-D stencil (dimension-generic form of StencilOperator2D)
+# ==========================================================================================
+class StencilOperatorND:
+    """Full d-dim stencil v[i] = sum_k S[i, k] u[i + k - p]; data (n1..nd, 2p1+1..2pd+1)."""
+
+    def __init__(self, data):
+        self.data = np.asarray(data, float)
+        d = self.data.ndim // 2
+        self.ndim = d
+        self.npts = tuple(self.data.shape[:d])
+        self.pads = tuple((w - 1) // 2 for w in self.data.shape[d:])
+        n = int(np.prod(self.npts))
+        self.shape = (n, n)
+
+    def dot(self, X):
+        d = self.ndim
+        Xp = np.zeros(tuple(n + 2 * p for n, p in zip(self.npts, self.pads)))
+        Xp[tuple(slice(p, p + n) for n, p in zip(self.npts, self.pads))] = X
+        Y = np.zeros(self.npts)
+        for ks in np.ndindex(*[2 * p + 1 for p in self.pads]):
+            Y += self.data[(Ellipsis,) + ks] * Xp[tuple(slice(k, k + n) for k, n in zip(ks, self.npts))]
+        return Y
+
+    def diagonal(self):
+        return self.data[(Ellipsis,) + tuple(self.pads)].copy()
+
+
+def gmres(A, b, x0=None, tol=1e-6, maxiter=100, restart=30, psolve=None):
+    """CPU restatement of poms_b200.solvers.gmres: restarted GMRES, right preconditioning, CGS2
+    Arnoldi, Givens least squares, stop at ||r|| <= tol ||r0||.  Returns (x, info)."""
+    x = np.zeros_like(b) if x0 is None else x0.copy()
+    niter, nrm0, res, hist = 0, None, None, []
+    while True:
+        r = b - A.dot(x)
+        beta = float(np.sqrt(np.vdot(r, r)))
+        if nrm0 is None:
+            nrm0 = beta
+        res = beta
+        if beta <= tol * nrm0 or niter >= maxiter or beta == 0.0:
+            break
+        basis = [r / beta]
+        H = np.zeros((restart + 1, restart))
+        cs, sn = np.zeros(restart), np.zeros(restart)
+        g = np.zeros(restart + 1)
+        g[0] = beta
+        k_used = 0
+        for k in range(restart):
+            z = psolve(A, basis[k]) if psolve is not None else basis[k]
+            w = A.dot(z)
+            h = np.array([np.vdot(w, v) for v in basis])
+            for hi, v in zip(h, basis):
+                w = w - hi * v
+            h2 = np.array([np.vdot(w, v) for v in basis])
+            for hi, v in zip(h2, basis):
+                w = w - hi * v
+            h = h + h2
+            hk1 = float(np.sqrt(max(np.vdot(w, w), 0.0)))
+            H[:k + 1, k] = h
+            H[k + 1, k] = hk1
+            basis.append(w / hk1 if hk1 > 0 else w)
+            for i in range(k):
+                t = cs[i] * H[i, k] + sn[i] * H[i + 1, k]
+                H[i + 1, k] = -sn[i] * H[i, k] + cs[i] * H[i + 1, k]
+                H[i, k] = t
+            den = np.hypot(H[k, k], H[k + 1, k])
+            cs[k], sn[k] = (H[k, k] / den, H[k + 1, k] / den) if den > 0 else (1.0, 0.0)
+            H[k, k] = cs[k] * H[k, k] + sn[k] * H[k + 1, k]
+            H[k + 1, k] = 0.0
+            g[k + 1] = -sn[k] * g[k]
+            g[k] = cs[k] * g[k]
+            niter += 1
+            k_used = k + 1
+            res = abs(g[k + 1])
+            hist.append(res)
+            if res <= tol * nrm0 or niter >= maxiter or hk1 == 0.0:
+                break
+        yk = np.linalg.solve(np.triu(H[:k_used, :k_used]), g[:k_used]) if k_used else np.zeros(0)
+        u = np.zeros_like(b)
+        for yi, v in zip(yk, basis):
+            u = u + yi * v
+        x = x + (psolve(A, u) if psolve is not None else u)
+        if res <= tol * nrm0 or niter >= maxiter:
+            r = b - A.dot(x)
+            res = float(np.sqrt(np.vdot(r, r)))
+            if res <= tol * nrm0 or niter >= maxiter:
+                break
+    return x, {"niter": niter, "success": bool(res <= tol * nrm0), "res_norm": res, "res_norm0": nrm0,
+               "history": hist}
+
+
+def rb_jacobi(A, b, x0=None, tol=1e-6, maxiter=10, omega=2.0 / 3.0):
+    """CPU restatement of poms_b200.solvers.rb_jacobi (two-colour damped Jacobi)."""
+    D = A.diagonal()
+    x = np.zeros_like(b) if x0 is None else x0.copy()
+    idx = np.indices(b.shape).sum(axis=0)
+    tol_sqr = tol ** 2
+    for k in range(1, maxiter + 1):
+        tot = 0.0
+        for colour in (0, 1):
+            d = omega * (b - A.dot(x)) / D
+            tot += 0.5 * float(np.vdot(d, d))
+            mask = (idx & 1) == colour
+            x = x + np.where(mask, d, 0.0)
+        if tot < tol_sqr:
+            break
+    return x

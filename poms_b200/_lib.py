@@ -16,6 +16,9 @@ _PROTOS = {
     "poms_launch_count_add": (None, [_l]),
     "poms_kron_matvec_2d": (C.c_int, [_vp, _vp, _vp, _i, _i, _l, _i, _i, _i, _i,
                                      _vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp]),
+    "poms_kron_matvec_2d_ex": (C.c_int, [_vp, _vp, _vp, _i, _i, _l, _i, _i, _i, _i,
+                                        _vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp]),
+    "poms_set_matvec2d_variant": (None, [_i]),
     "poms_kron_matvec_3d": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _i,
                                      _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp]),
     "poms_kron_matvec_3d_ex": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _i,
@@ -48,6 +51,9 @@ _PROTOS = {
                                   _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "poms_prolong_3d": (C.c_int, [_vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _l, _l,
                                  _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "poms_stencil_matvec_3d": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _i, _i,
+                                        _i, _d, _vp, _vp, _vp]),
+    "poms_color_add": (C.c_int, [_vp, _vp, _i, _i, _i, _l, _l, _i, _i, _vp]),
     "poms_axis_dense_dmma": (C.c_int, [_vp, _vp, _vp, _i, _i, _l, _l, _l, _l, _l, _l, _vp]),
     "poms_ipc_alloc": (C.c_int, [_l, C.POINTER(C.c_void_p)]),
     "poms_ipc_free": (C.c_int, [_vp]),

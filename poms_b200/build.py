@@ -14,7 +14,7 @@ SRC = os.path.join(CSRC, "poms_kernels.cu")
 EXTRA_SRC = [os.path.join(CSRC, "poms_extra.cu")]      # self-contained units (own kernels + C ABI)
 OUT = os.path.join(HERE, "libpoms_b200.so")
 OBJDIR = os.path.join(ROOT, "build", "obj")
-TUS = [0, 1, 2, 3, 4, 5, 6]
+TUS = [0, 1, 2, 3, 4, 5, 6, 7]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-diag-suppress", "177,550",

@@ -2,15 +2,13 @@
 // include/poms_b200.h):
 //   * peer-memory halo exchange over NVLink (CUDA IPC): replaces the NCCL send/recv pair behind
 //     `update_ghost_regions` (/root/reference/sources/kron_product.py:76,87, solvers.py:162,215)
-#include <cuda_runtime.h>
-#include <stdint.h>
-#include <stdio.h>
+//   * dense per-axis contraction on the fp64 tensor cores (DMMA)
+//   * full (non-separable) 3-D stencil mat-vec, two-colour Jacobi update
 #include <string.h>
-#include "poms_b200.h"
-
-#define POMS_HIDDEN __attribute__((visibility("hidden")))
-extern POMS_HIDDEN thread_local char g_err[256];
-extern POMS_HIDDEN int64_t g_launches;
+// shared helpers (error text, launch counter, deterministic grid reduction): the common part of
+// poms_kernels.cu, none of its translation-unit sections
+#define POMS_TU 99
+#include "poms_kernels.cu"
 
 static int x_fail_cuda(cudaError_t e, const char* where) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
@@ -270,5 +268,148 @@ extern "C" int poms_axis_dense_dmma(const double* in, double* out, const double*
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return x_fail_cuda(e, "poms_axis_dense_dmma");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Full (non-separable) 3-D stencil mat-vec: y[i] = sum_k S[i, k1, k2, k3] x[i + k - p]
+// = spl StencilMatrix.dot in 3-D (slides/content.tex:285-290; the operator the reference's solvers
+// call, sources/solvers.py:85,103,209).  S is (n1, n2, n3, 2p1+1, 2p2+1, 2p3+1) row-major: (2p+1)^3
+// coefficients PER ROW (343 doubles = 2.7 KB at p = 3), so the kernel is bound by the coefficient
+// stream, not by x: one WARP per output point, lanes stride over the point's contiguous coefficient
+// block (coalesced 256-byte requests), x comes from L1/L2, warp-shuffle sum.
+// ------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(256) stencil_matvec3d_kernel(
+    const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
+    const double* __restrict__ S, int n1, int n2, int n3, int64_t ld, int64_t pld, int glo, int ghi, int p1, int p2,
+    int p3, double omega, double* dot_out, void* ws) {
+    __shared__ double red[32];
+    extern __shared__ int soff[];          // per coefficient: offset of its x entry relative to the point
+    const int W2 = 2 * p2 + 1, W3 = 2 * p3 + 1, NC = (2 * p1 + 1) * W2 * W3;
+    const int lane = threadIdx.x & 31;
+    for (int c = threadIdx.x; c < NC; c += blockDim.x) {
+        const int k3 = c % W3, k2 = (c / W3) % W2, k1 = c / (W3 * W2);
+        soff[c] = (int)((k1 - p1) * pld + (k2 - p2) * ld + (k3 - p3));
+    }
+    __syncthreads();
+    const int64_t npts = (int64_t)n1 * n2 * n3;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    double dsum = 0.0;
+    for (int64_t pt = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pt < npts; pt += nwarps) {
+        const int i3 = (int)(pt % n3);
+        const int i2 = (int)((pt / n3) % n2);
+        const int i1 = (int)(pt / ((int64_t)n3 * n2));
+        const double* Sp = S + pt * NC;
+        const double* xp = x + ((int64_t)i1 * pld + (int64_t)i2 * ld + i3);
+        double v = 0.0;
+        // interior points (the whole stencil inside the stored planes): no bounds checks
+        const bool inner = i1 - p1 >= -glo && i1 + p1 < n1 + ghi && i2 >= p2 && i2 + p2 < n2 && i3 >= p3 &&
+                           i3 + p3 < n3;
+        if (inner) {
+            double v1 = 0.0;
+            int c = lane;
+            for (; c + 32 < NC; c += 64) {
+                v = fma(__ldg(Sp + c), xp[soff[c]], v);
+                v1 = fma(__ldg(Sp + c + 32), xp[soff[c + 32]], v1);
+            }
+            if (c < NC) v = fma(__ldg(Sp + c), xp[soff[c]], v);
+            v += v1;
+        } else {
+            for (int c = lane; c < NC; c += 32) {
+                const int k3 = c % W3, k2 = (c / W3) % W2, k1 = c / (W3 * W2);
+                const int j1 = i1 + k1 - p1, j2 = i2 + k2 - p2, j3 = i3 + k3 - p3;
+                if (j1 >= -glo && j1 < n1 + ghi && j2 >= 0 && j2 < n2 && j3 >= 0 && j3 < n3)
+                    v = fma(__ldg(Sp + c), xp[soff[c]], v);
+            }
+        }
+        v = warp_sum(v);
+        if (lane == 0) {
+            const int64_t o = (int64_t)i1 * pld + (int64_t)i2 * ld + i3;
+            if (EPI == POMS_EPI_STORE) {
+                y[o] = v;
+                if (dot_out) dsum = fma(x[o], v, dsum);
+            } else if (EPI == POMS_EPI_RESID) {
+                const double rr = b[o] - v;
+                y[o] = rr;
+                dsum = fma(rr, rr, dsum);
+            } else if (EPI == POMS_EPI_AXPY) {
+                const double w_ = omega * v;
+                y[o] = b ? b[o] + w_ : w_;
+                dsum = fma(w_, w_, dsum);
+            } else {
+                const double dg = Sp[(p1 * W2 + p2) * W3 + p3];
+                const double dr = omega * (b[o] - v) / dg;
+                y[o] = (EPI == POMS_EPI_JACOBI) ? x[o] + dr : dr;
+                dsum = fma(dr, dr, dsum);
+            }
+        }
+    }
+    if (dot_out) {
+        const double tot = block_sum(dsum, red);
+        grid_sum_finish(tot, dot_out, ws, gridDim.x, blockIdx.x, red);
+    }
+}
+
+extern "C" int poms_stencil_matvec_3d(const double* x, double* y, const double* b, const double* S, int n1, int n2,
+                                      int n3, int64_t ld, int64_t pld, int glo, int ghi, int p1, int p2, int p3,
+                                      int epilogue, double omega, double* dot_out, void* ws, void* stream) {
+    if (!x) return bad_arg(1, "x");
+    if (!y) return bad_arg(2, "y");
+    if (epilogue != POMS_EPI_STORE && epilogue != POMS_EPI_AXPY && !b) return bad_arg(3, "b required by epilogue");
+    if (!S) return bad_arg(4, "S");
+    if (n1 < 1 || n2 < 1 || n3 < 1) return bad_arg(5, "extent");
+    if (ld < n3) return bad_arg(8, "ld");
+    if (pld < ld * n2) return bad_arg(9, "pld");
+    if (p1 < 0 || p2 < 0 || p3 < 0 || p1 > 5 || p2 > 5 || p3 > 5) return bad_arg(12, "pads");
+    if (dot_out && !ws) return bad_arg(18, "ws");
+    const int64_t npts = (int64_t)n1 * n2 * n3;
+    int64_t blocks = (npts + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = sizeof(int) * (size_t)(2 * p1 + 1) * (2 * p2 + 1) * (2 * p3 + 1);
+    if (pld * (int64_t)(p1 + 1) > 0x7fffffff) return bad_arg(9, "plane pitch too large for 32-bit stencil offsets");
+#define POMS_S3(E) stencil_matvec3d_kernel<E><<<(int)blocks, 256, smem, st>>>(x, y, b, S, n1, n2, n3, ld, pld, glo, ghi, p1, p2, p3, omega, dot_out, ws)
+    switch (epilogue) {
+        case POMS_EPI_STORE: POMS_S3(POMS_EPI_STORE); break;
+        case POMS_EPI_RESID: POMS_S3(POMS_EPI_RESID); break;
+        case POMS_EPI_JACOBI: POMS_S3(POMS_EPI_JACOBI); break;
+        case POMS_EPI_DINV: POMS_S3(POMS_EPI_DINV); break;
+        case POMS_EPI_AXPY: POMS_S3(POMS_EPI_AXPY); break;
+        default: return bad_arg(15, "epilogue");
+    }
+#undef POMS_S3
+    CHECK_LAUNCH("poms_stencil_matvec_3d");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Two-colour (red-black) update x[i] += d[i] on the points with (i1 + i2 [+ i3] + off) % 2 == colour:
+// the half sweep of a red-black damped Jacobi smoother (named as future work in the reference's
+// slides, slides/content.tex:393).  d = omega D^-1 (b - A x) comes from the fused DINV epilogue.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) color_add_kernel(double* __restrict__ x, const double* __restrict__ d, int n1,
+                                                        int n2, int n3, int64_t ld, int64_t pld, int off, int colour) {
+    const int64_t total = (int64_t)n1 * n2 * n3;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int i3 = (int)(t % n3);
+        const int i2 = (int)((t / n3) % n2);
+        const int i1 = (int)(t / ((int64_t)n3 * n2));
+        if (((i1 + i2 + i3 + off) & 1) == colour) {
+            const int64_t o = (int64_t)i1 * pld + (int64_t)i2 * ld + i3;
+            x[o] += d[o];
+        }
+    }
+}
+extern "C" int poms_color_add(double* x, const double* d, int n1, int n2, int n3, int64_t ld, int64_t pld, int off,
+                              int colour, void* stream) {
+    if (!x || !d) return bad_arg(1, "null pointer");
+    if (n1 < 1 || n2 < 1 || n3 < 1) return bad_arg(3, "extent");
+    const int64_t total = (int64_t)n1 * n2 * n3;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    color_add_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, d, n1, n2, n3, ld, pld, off, colour & 1);
+    CHECK_LAUNCH("poms_color_add");
     return 0;
 }

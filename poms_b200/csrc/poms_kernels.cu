@@ -162,6 +162,41 @@ __device__ __forceinline__ void rot_scatter(int u, double (&acc)[E][W], const do
     }
 }
 
+// Axis-1 partial sums in SHIFT form: after input plane j, acc[e][m] is the partial sum of output plane
+// j - P + m.  Plane j adds c[W-1-m] * value to it; in place that reads acc[m+1] (the same output one
+// plane earlier) and writes acc[m], for ascending m, so the window slides without a rotation index,
+// without register moves and without the 7-way switch of rot_scatter: one straight-line block of
+// W (2W for the sum form) independent FMA chains per point.  The completed plane is acc[e][0].
+template <int W, int E, bool TWO>
+__device__ __forceinline__ void shift_scatter(double (&acc)[E][W], const double (&ta)[E], const double (&tb)[E],
+                                              const double (&c1k)[W], const double (&c1m)[W], double (&vout)[E]) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+#pragma unroll
+        for (int m = 0; m < W - 1; ++m) {
+            acc[e][m] = fma(c1k[W - 1 - m], ta[e], acc[e][m + 1]);
+            if (TWO) acc[e][m] = fma(c1m[W - 1 - m], tb[e], acc[e][m]);
+        }
+        acc[e][W - 1] = c1k[0] * ta[e];
+        if (TWO) acc[e][W - 1] = fma(c1m[0], tb[e], acc[e][W - 1]);
+        vout[e] = acc[e][0];
+    }
+}
+
+struct MV2 {
+    const double* x;
+    double* y;
+    const double* b;
+    int n1, n2;
+    int64_t ld;
+    int glo, ghi;
+    const double *m1, *k1, *m2, *k2;
+    double omega;
+    double* dot_out;
+    void* ws;
+    int chunk;
+};
+
 // ------------------------------------------------------------------------------------------
 // K1: Kronecker banded mat-vec, 3-D
 // ------------------------------------------------------------------------------------------
@@ -416,6 +451,19 @@ static int pick_chunk(int n1, int64_t tiles, int p) {
 #include "poms_matvec3d_tma.cuh"
 
 #if POMS_TU == 0
+// axis-1 chunk of the 2-D TMA kernel: ~2 waves of 148 SMs x 5 CTAs, at least 12p rows per chunk
+static int pick_chunk2d(int n1, int64_t strips, int p) {
+    int64_t nch = (148 * 5 * 2 + strips - 1) / strips;
+    if (nch < 1) nch = 1;
+    int chunk = (int)((n1 + nch - 1) / nch);
+    if (chunk < 12 * p) chunk = 12 * p;
+    if (chunk > n1) chunk = n1;
+    return chunk;
+}
+#endif
+#include "poms_matvec2d_tma.cuh"
+
+#if POMS_TU == 0
 
 extern "C" int poms_kron_matvec_3d_ex(const double* x, double* y, const double* b, int n1, int n2,
                                       int n3, int64_t ld, int64_t pld, int glo, int ghi, int p,
@@ -484,19 +532,6 @@ extern "C" int poms_kron_matvec_3d_ex(const double* x, double* y, const double* 
 // K1: Kronecker banded mat-vec, 2-D.  CTA = 128 threads x E columns, marches along axis 1 in
 // batches of RB rows per barrier.
 // ------------------------------------------------------------------------------------------
-struct MV2 {
-    const double* x;
-    double* y;
-    const double* b;
-    int n1, n2;
-    int64_t ld;
-    int glo, ghi;
-    const double *m1, *k1, *m2, *k2;
-    double omega;
-    double* dot_out;
-    void* ws;
-    int chunk;
-};
 
 template <int P, int FORM, int EPI>
 __global__ void __launch_bounds__(128, 4) kron_matvec2d_kernel(MV2 a) {
@@ -637,11 +672,12 @@ static int launch_mv2(const MV2& a, int form, int epi, dim3 grid, cudaStream_t s
     return bad_arg(10, "form");
 }
 
-extern "C" int poms_kron_matvec_2d(const double* x, double* y, const double* b, int n1, int n2,
-                                   int64_t ld, int glo, int ghi, int p, int form,
-                                   const double* m1, const double* k1, const double* m2,
-                                   const double* k2, int epilogue, double omega,
-                                   double* dot_out, void* ws, void* stream) {
+extern "C" int poms_kron_matvec_2d_ex(const double* x, double* y, const double* b, int n1, int n2,
+                                      int64_t ld, int glo, int ghi, int p, int form,
+                                      const double* m1, const double* k1, const double* m2,
+                                      const double* k2, int epilogue, double omega,
+                                      double* dot_out, void* ws, void* stream,
+                                      const double* toep_host, const int* toep_rng_host) {
     if (!x) return bad_arg(1, "x");
     if (!y) return bad_arg(2, "y");
     if (epilogue != POMS_EPI_STORE && epilogue != POMS_EPI_AXPY && !b) return bad_arg(3, "b required by epilogue");
@@ -651,7 +687,18 @@ extern "C" int poms_kron_matvec_2d(const double* x, double* y, const double* b, 
     if (!m1 || !m2) return bad_arg(11, "band pointers");
     if (form == POMS_FORM_SUM && (!k1 || !k2)) return bad_arg(12, "k bands");
     if (dot_out && !ws) return bad_arg(18, "ws");
+    if (p < 1 || p > 5) return bad_arg(9, "p must be 1..5");
+    if (form != POMS_FORM_SINGLE && form != POMS_FORM_SUM) return bad_arg(10, "form");
     MV2 a{x, y, b, n1, n2, ld, glo, ghi, m1, k1, m2, k2, omega, dot_out, ws, 0};
+    {
+        // fast path: warp-autonomous TMA kernel (16-byte aligned rows); 1 = not applicable
+        const int trc = try_matvec2d_tma(a, p, form, epilogue, toep_host, toep_rng_host, (cudaStream_t)stream);
+        if (trc == 0) {
+            CHECK_LAUNCH("poms_kron_matvec_2d(tma)");
+            return 0;
+        }
+        if (trc != 1) return trc;
+    }
     const int g2 = (n2 + 255) / 256;
     a.chunk = pick_chunk(n1, g2, p);
     const int g1 = (n1 + a.chunk - 1) / a.chunk;
@@ -670,6 +717,15 @@ extern "C" int poms_kron_matvec_2d(const double* x, double* y, const double* b, 
     if (rc) return rc;
     CHECK_LAUNCH("poms_kron_matvec_2d");
     return 0;
+}
+
+extern "C" int poms_kron_matvec_2d(const double* x, double* y, const double* b, int n1, int n2,
+                                   int64_t ld, int glo, int ghi, int p, int form,
+                                   const double* m1, const double* k1, const double* m2,
+                                   const double* k2, int epilogue, double omega,
+                                   double* dot_out, void* ws, void* stream) {
+    return poms_kron_matvec_2d_ex(x, y, b, n1, n2, ld, glo, ghi, p, form, m1, k1, m2, k2, epilogue, omega,
+                                  dot_out, ws, stream, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------

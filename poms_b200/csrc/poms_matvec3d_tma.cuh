@@ -603,6 +603,14 @@ static int try_matvec3d_tma(const MV3& a0, int p, int form, int epilogue, const 
         if (!sym || (need_b && ((uintptr_t)a0.b & 15))) {
             var = 0;
         } else {
+            // the pair-sum form uses the MEAN of the two halves of a row, so that row sums (K 1 = 0,
+            // partition of unity) carry no systematic bias from the rounding-level asymmetry
+            if (form == POMS_FORM_SUM) {
+                double* rows[4] = {g.t2m, g.t2k, g.t3m, g.t3k};
+                for (int r = 0; r < 4; ++r)
+                    for (int k = 1; k <= p; ++k)
+                        rows[r][p + k] = rows[r][p - k] = 0.5 * (rows[r][p + k] + rows[r][p - k]);
+            }
             if (need_b) {
                 if (get_tmap(enc, a0.b, a0.n3, a0.n2, a0.n1, a0.ld, a0.pld, 64 + 2 * sh, 16, &tm3[1])) return 1;
                 ++ntiles;

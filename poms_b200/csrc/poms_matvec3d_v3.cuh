@@ -24,27 +24,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
-// Axis-1 partial sums in SHIFT form: after input plane j, acc[e][m] is the partial sum of output plane
-// j - P + m.  Plane j adds c[W-1-m] * value to it; in place that reads acc[m+1] (the same output one
-// plane earlier) and writes acc[m], for ascending m, so the window slides without a rotation index,
-// without register moves and without the 7-way switch of rot_scatter: one straight-line block of
-// W (2W for the sum form) independent FMA chains per point.  The completed plane is acc[e][0].
-template <int W, int E, bool TWO>
-__device__ __forceinline__ void shift_scatter(double (&acc)[E][W], const double (&ta)[E], const double (&tb)[E],
-                                              const double (&c1k)[W], const double (&c1m)[W], double (&vout)[E]) {
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-#pragma unroll
-        for (int m = 0; m < W - 1; ++m) {
-            acc[e][m] = fma(c1k[W - 1 - m], ta[e], acc[e][m + 1]);
-            if (TWO) acc[e][m] = fma(c1m[W - 1 - m], tb[e], acc[e][m]);
-        }
-        acc[e][W - 1] = c1k[0] * ta[e];
-        if (TWO) acc[e][W - 1] = fma(c1m[0], tb[e], acc[e][W - 1]);
-        vout[e] = acc[e][0];
-    }
-}
-
 template <int P>
 struct MV3V3Cfg : MV3TCfg<P> {
     using B = MV3TCfg<P>;

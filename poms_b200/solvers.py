@@ -11,6 +11,8 @@ residual histories can be compared with the oracle; the reference only prints th
 """
 from math import sqrt
 
+import numpy as np
+
 import torch
 
 from . import _lib
@@ -18,7 +20,7 @@ from . import profiling
 from .stencil import (StencilVector, DeviceContext, dot_into, _stream, EPI_STORE, EPI_RESID,
                       EPI_JACOBI)
 
-__all__ = ["crl", "pcg", "jacobi", "damped_jacobi", "pcg_glt"]
+__all__ = ["crl", "pcg", "jacobi", "damped_jacobi", "pcg_glt", "gmres", "rb_jacobi"]
 
 # device scalar slots (DeviceContext.scal)
 S_TMP, S_RR, S_PQ, S_SR0, S_SR1, S_DR, S_QQ = 0, 1, 2, 3, 4, 5, 6
@@ -226,3 +228,138 @@ def crl(A, b, x0=None, tol=1e-5, maxiter=1000, verbose=False):
             print("| {:7d} | {:19.2e} |".format(k, sqrt(sr)))
     info = {"niter": k, "success": sr < tol_sqr, "res_norm": sqrt(max(sr, 0.0))}
     return x, info
+
+
+# ==========================================================================================
+# EXTENSION: the two solvers the reference names as future work (slides/content.tex:393-394)
+# ==========================================================================================
+S_GM0 = 16          # first of the device scalar slots used by gmres (one per Krylov vector)
+
+
+def gmres(A, b, x0=None, tol=1e-6, maxiter=100, restart=30, psolve=None, verbose=False):
+    """Restarted GMRES(restart) with RIGHT preconditioning (x = x0 + M^-1 V y, so the monitored
+    norm is the true residual's), Arnoldi by classical Gram-Schmidt applied twice (CGS2: all
+    inner products of a pass are queued on the device and read back together, two host reads per
+    step instead of one per basis vector).  `psolve(A, v) -> M^-1 v` must be a fixed linear map.
+    Stops when ||r|| <= tol * ||r0||.  Returns (x, info) like pcg; niter counts mat-vecs of the
+    Arnoldi process.  The test suite checks it against a NumPy restatement of the same operations."""
+    _check_shapes(A, b, x0)
+    assert 1 <= restart <= 40
+    V = b.space
+    ctx = DeviceContext.get(V.device)
+    L = _lib.lib()
+    st = _stream
+
+    def axpby(z, a_, x_, b_, y_):
+        _lib.check(L.poms_axpby(z.ptr, float(a_), x_.ptr, float(b_), y_.ptr if y_ is not None else None,
+                                z.n_owned, st()), "poms_axpby")
+
+    def dots(w, basis):
+        for i, v in enumerate(basis):
+            dot_into(w, v, ctx.sptr(S_GM0 + i), ctx)
+        h = ctx.scal[S_GM0:S_GM0 + len(basis)]
+        if V.slab is not None and V.slab.size > 1:
+            V.slab.allreduce_sum(h)
+        return h.cpu().numpy().copy()
+
+    x = StencilVector(V) if x0 is None else x0.copy()
+    r = StencilVector(V, zero=False)
+    w = StencilVector(V, zero=False)
+    basis = [StencilVector(V, zero=False) for _ in range(restart + 1)]
+    niter, nrm0, res = 0, None, None
+    hist = []
+    while True:
+        A.apply(x, r, EPI_RESID, b=b, dot_ptr=ctx.sptr(S_RR))
+        beta = sqrt(_read(ctx, V, S_RR))
+        if nrm0 is None:
+            nrm0 = beta
+        res = beta
+        if beta <= tol * nrm0 or niter >= maxiter or beta == 0.0:
+            break
+        axpby(basis[0], 1.0 / beta, r, 0.0, None)
+        H = np.zeros((restart + 1, restart))
+        cs, sn = np.zeros(restart), np.zeros(restart)
+        g = np.zeros(restart + 1)
+        g[0] = beta
+        k_used = 0
+        for k in range(restart):
+            z = psolve(A, basis[k]) if psolve is not None else basis[k]
+            A.apply(z, w, EPI_STORE)
+            h = dots(w, basis[:k + 1])
+            for i in range(k + 1):
+                axpby(w, 1.0, w, -h[i], basis[i])
+            h2 = dots(w, basis[:k + 1])
+            for i in range(k + 1):
+                axpby(w, 1.0, w, -h2[i], basis[i])
+            h = h + h2
+            hk1 = sqrt(max(w.dot(w), 0.0))
+            H[:k + 1, k] = h
+            H[k + 1, k] = hk1
+            if hk1 > 0.0:
+                axpby(basis[k + 1], 1.0 / hk1, w, 0.0, None)
+            for i in range(k):                                # earlier Givens rotations
+                t = cs[i] * H[i, k] + sn[i] * H[i + 1, k]
+                H[i + 1, k] = -sn[i] * H[i, k] + cs[i] * H[i + 1, k]
+                H[i, k] = t
+            den = np.hypot(H[k, k], H[k + 1, k])
+            cs[k], sn[k] = (H[k, k] / den, H[k + 1, k] / den) if den > 0 else (1.0, 0.0)
+            H[k, k] = cs[k] * H[k, k] + sn[k] * H[k + 1, k]
+            H[k + 1, k] = 0.0
+            g[k + 1] = -sn[k] * g[k]
+            g[k] = cs[k] * g[k]
+            niter += 1
+            k_used = k + 1
+            res = abs(g[k + 1])
+            hist.append(res)
+            if verbose:
+                print("| {:7d} | {:19.2e} |".format(niter, res))
+            if res <= tol * nrm0 or niter >= maxiter or hk1 == 0.0:
+                break
+        yk = np.linalg.solve(np.triu(H[:k_used, :k_used]), g[:k_used]) if k_used else np.zeros(0)
+        axpby(w, yk[0], basis[0], 0.0, None)
+        for i in range(1, k_used):
+            axpby(w, 1.0, w, yk[i], basis[i])
+        upd = psolve(A, w) if psolve is not None else w
+        axpby(x, 1.0, x, 1.0, upd)
+        if res <= tol * nrm0 or niter >= maxiter:
+            A.apply(x, r, EPI_RESID, b=b, dot_ptr=ctx.sptr(S_RR))
+            res = sqrt(_read(ctx, V, S_RR))
+            if res <= tol * nrm0 or niter >= maxiter:
+                break
+    info = {"niter": niter, "success": bool(res <= tol * nrm0), "res_norm": res, "res_norm0": nrm0,
+            "history": hist}
+    return x, info
+
+
+def rb_jacobi(A, b, x0=None, tol=1e-6, maxiter=10, omega=2.0 / 3.0, verbose=False):
+    """Two-colour (red-black) damped Jacobi: every sweep updates the points with even i1+i2(+i3)
+    from the current residual, then the odd ones from the refreshed residual,
+        x_c += omega D^-1 (b - A x)_c ,   c = red, black
+    (two fused residual passes per sweep; each half sweep is a Jacobi step on half of the
+    unknowns, so omega = 2/3 is stable where the plain sweep of damped_jacobi is not, DESIGN.md
+    section 2).  Stops like damped_jacobi when the update of a sweep has ||d||^2 < tol^2; returns x
+    only, like damped_jacobi (/root/reference/sources/solvers.py:235).  Checked against a NumPy
+    restatement by the test suite."""
+    _check_shapes(A, b, x0)
+    V = b.space
+    ctx = DeviceContext.get(V.device)
+    L = _lib.lib()
+    x = StencilVector(V) if x0 is None else x0.copy()
+    d = StencilVector(V, zero=False)
+    shp = tuple(V.local_shape)
+    n1, n2, n3 = (1,) * (3 - len(shp)) + shp
+    pld = x.pld if len(shp) == 3 else n2 * x.ld
+    off = V.starts[0]                      # global index of the first owned plane / row
+    tol_sqr = tol ** 2
+    for k in range(1, maxiter + 1):
+        tot = 0.0
+        for colour in (0, 1):
+            A.apply(x, d, EPI_DINV, b=b, omega=omega, dot_ptr=ctx.sptr(S_DR))
+            tot += 0.5 * _read(ctx, V, S_DR)
+            _lib.check(L.poms_color_add(x.ptr, d.ptr, n1, n2, n3, x.ld, pld, off, colour, _stream()),
+                       "poms_color_add")
+        if verbose:
+            print("| {:7d} | {:19.2e} |".format(k, sqrt(tot)))
+        if tot < tol_sqr:
+            break
+    return x

@@ -453,8 +453,8 @@ class StencilMatrix:
     def __init__(self, V, W=None):
         W = W or V
         assert V.npts == W.npts and V.pads == W.pads
-        if V.ndim not in (1, 2):
-            raise NotImplementedError("StencilMatrix: 1-D bands or full 2-D stencils")
+        if V.ndim not in (1, 2, 3):
+            raise NotImplementedError("StencilMatrix: 1-D bands or full 2-D / 3-D stencils")
         self._domain, self._codomain = V, W
         self.ndim = V.ndim
         self.starts = tuple(0 for _ in V.npts)
@@ -553,12 +553,22 @@ class StencilMatrix:
         return self._slab_dev[key]
 
     def apply(self, x, y, epi=EPI_STORE, b=None, omega=0.0, dot_ptr=None):
-        assert self.ndim == 2
+        assert self.ndim in (2, 3)
         V = x.space
         if V.slab is not None:
             V.slab.exchange(x)
         ctx = DeviceContext.get(V.device)
         S = self._rows_for(V)
+        if self.ndim == 3:
+            # full 3-D stencil ((2p+1)^3 coefficients per row): EXTENSION of the reference's 2-D type
+            n1, n2, n3 = V.local_shape
+            nbytes = 8 * S.numel() + 16 * V.local_size
+            with profiling.region("stencil_matvec_3d", nbytes):
+                _lib.check(_lib.lib().poms_stencil_matvec_3d(
+                    x.ptr, y.ptr, b.ptr if b is not None else None, S.data_ptr(), n1, n2, n3, x.ld, x.pld,
+                    V.glo, V.ghi, self.pads[0], self.pads[1], self.pads[2], epi, float(omega), dot_ptr,
+                    ctx.ws_ptr, _stream()), "poms_stencil_matvec_3d")
+            return
         n1, n2 = V.local_shape
         _lib.check(_lib.lib().poms_stencil_matvec_2d(
             x.ptr, y.ptr, b.ptr if b is not None else None, S.data_ptr(), n1, n2, x.ld,
@@ -566,8 +576,8 @@ class StencilMatrix:
             _stream()), "poms_stencil_matvec_2d")
 
     def dot(self, v):
-        if self.ndim != 2:
-            raise NotImplementedError("StencilMatrix.dot: 2-D stencils (1-D factors are applied "
+        if self.ndim not in (2, 3):
+            raise NotImplementedError("StencilMatrix.dot: 2-D / 3-D stencils (1-D factors are applied "
                                       "through kron_dot / KronSumMatrix)")
         out = StencilVector(v.space)
         self.apply(v, out)
@@ -575,8 +585,8 @@ class StencilMatrix:
 
     def diagonal_vector(self, V):
         d = StencilVector(V)
-        p1, p2 = self.pads
-        loc = np.ascontiguousarray(self._data[V.starts[0]:V.ends[0] + 1, :, p1, p2])
+        centre = (slice(V.starts[0], V.ends[0] + 1),) + (slice(None),) * (self.ndim - 1) + tuple(self.pads)
+        loc = np.ascontiguousarray(self._data[centre])
         d.flat.fill_(1.0)          # pad column: 0/1 keeps the pad at zero
         d.data.copy_(torch.as_tensor(loc, device=V.device))
         return d
@@ -722,10 +732,15 @@ class KronSumMatrix:
         if self.ndim == 2:
             n1, n2 = V.local_shape
             assert z0 == 0 and z1 is None
-            _lib.check(L.poms_kron_matvec_2d(
+            coef, rng = self._toeplitz()
+            rng = rng.copy()
+            # axis-1 rows are the slab's: shift the global interior range to local row numbers
+            rng[0] = max(0, int(rng[0]) - V.starts[0])
+            rng[1] = max(int(rng[0]), min(n1, int(rng[1]) - V.starts[0]))
+            _lib.check(L.poms_kron_matvec_2d_ex(
                 x.ptr, y.ptr, bp, n1, n2, x.ld, V.glo, V.ghi, self.P, self.form,
                 m[0].data_ptr(), kp[0], m[1].data_ptr(), kp[1], epi, float(omega), dot_ptr,
-                ctx.ws_ptr, _stream()), "poms_kron_matvec_2d")
+                ctx.ws_ptr, _stream(), coef.ctypes.data, rng.ctypes.data), "poms_kron_matvec_2d")
         else:
             n1, n2, n3 = V.local_shape
             z1 = n1 if z1 is None else z1
@@ -802,9 +817,19 @@ class KronSumMatrix:
         return tot
 
     def to_stencil_array(self):
-        """Full (n1, n2, 2P+1, 2P+1) stencil of the 2-D operator (host, tests)."""
-        assert self.ndim == 2
+        """Full (n1, .., nd, 2P+1, .., 2P+1) stencil of the operator (host, tests)."""
+        d = self.ndim
+
+        def outer(bands):
+            t = np.ones(())
+            for a, bnd in enumerate(bands):
+                shp = [1] * (2 * d)
+                shp[a], shp[d + a] = bnd.shape
+                t = t * bnd.reshape(shp)
+            return t
         if self.form == FORM_SINGLE:
-            return self.Ms[0][:, None, :, None] * self.Ms[1][None, :, None, :]
-        return (self.Ks[0][:, None, :, None] * self.Ms[1][None, :, None, :]
-                + self.Ms[0][:, None, :, None] * self.Ks[1][None, :, None, :])
+            return outer(self.Ms)
+        tot = 0.0
+        for a in range(d):
+            tot = tot + outer([self.Ks[c] if c == a else self.Ms[c] for c in range(d)])
+        return tot
