@@ -232,6 +232,12 @@ def main():
     ap.add_argument("--rhs", default="auto", choices=["auto", "ones", "manufactured"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
+                    help="N > 1: weak = N element planes per GPU along axis 1 (c5: BASELINE's weak-scaling "
+                         "sweep), strong = the named grid split into slabs (c4: BASELINE config 4, "
+                         "sources/scalability.py:7-19); auto = strong for c4, weak otherwise")
+    ap.add_argument("--setup", default="host", choices=["host", "device"],
+                    help="where the 1-D setup of the hierarchy runs (device: csrc/poms_setup.cu)")
     ap.add_argument("--no-exact-glt", action="store_true",
                     help="skip the extra solves with the reference's exact GLT smoother (N=1 only)")
     args = ap.parse_args()
@@ -265,11 +271,12 @@ def main():
     ndim, p, N, desc = CONFIGS[args.config]
     args.smoother = resolve_smoother(args.smoother, p)
     Ns = [N] * ndim
-    if world > 1:
+    scaling = args.scaling if args.scaling != "auto" else ("strong" if args.config == "c4" else "weak")
+    if world > 1 and scaling == "weak":
         Ns[0] = N * world          # weak scaling: N element planes per GPU along axis 1
     # weak scaling: the domain grows with the grid, [0, G] x [0,1]^(d-1), so the elements stay cubes
     # (keeping [0,1]^d would make the global problem anisotropic and change the iteration count)
-    lengths = [float(world)] + [1.0] * (ndim - 1)
+    lengths = [float(world) if scaling == "weak" else 1.0] + [1.0] * (ndim - 1)
     # coarsest level: solved exactly by fast diagonalisation, so it need not be tiny; stopping at 32
     # elements per axis in 3-D saves two levels of launch-latency-bound kernels per V-cycle
     # The same coarsest grid at every GPU count (32 elements per axis per GPU in 3-D): with slabs the
@@ -278,9 +285,23 @@ def main():
     Nc = args.nc if args.nc > 0 else (32 if ndim == 3 else 8)
     t_setup = time.perf_counter()
     h = Hierarchy(p, Ns, device=dev, smoother=args.smoother, nu=args.nu, slab=slab,
-                  lengths=lengths, Nc=Nc, coarsen="uniform")
+                  lengths=lengths, Nc=Nc, coarsen="uniform", setup=args.setup)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
+    t_setup_other = None
+    if world == 1:
+        # the other setup mode, timed for the record (its hierarchy is dropped: work vectors are lazy)
+        other = "device" if args.setup == "host" else "host"
+        try:
+            if other == "device":           # first use compiles nothing but loads kernels / cuSOLVER: warm
+                Hierarchy(p, [16] * ndim, device=dev, smoother=args.smoother, Nc=8, setup="device")
+            t0 = time.perf_counter()
+            Hierarchy(p, Ns, device=dev, smoother=args.smoother, nu=args.nu, lengths=lengths, Nc=Nc,
+                      coarsen="uniform", setup=other)
+            torch.cuda.synchronize()
+            t_setup_other = (other, round(time.perf_counter() - t0, 3))
+        except Exception as exc:             # informational
+            t_setup_other = (other, "failed: %r" % (exc,))
     V = h.levels[0].V
     dof_global = int(np.prod(V.npts))
     b = StencilVector(V)
@@ -457,8 +478,9 @@ def main():
     line = {
         "metric": METRIC, "value": dof_global / (ms * 1e-3), "unit": "DOF/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc + (" per GPU, slab-partitioned along axis 1" if world > 1
+        "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc + ((" per GPU, slab-partitioned along axis 1" if scaling == "weak"
+                                        else " split into %d slabs along axis 1" % world) if world > 1
                                        else ""),
                    "ndim": ndim, "p": p, "elements": Ns, "dof": dof_global, "domain": lengths,
                    "solver": "pcg + V(%d,%d) %s-Chebyshev multigrid, tol 1e-10 relative"
@@ -467,7 +489,8 @@ def main():
                                      "Kronecker solve, an EXTENSION (DESIGN.md section 3); `exact_glt` "
                                      "carries the same solve with the reference's exact GLT smoother")
                                     if args.smoother == "glt_poly" else "reference smoother family",
-                   "setup_seconds": round(t_setup, 3),
+                   "setup_seconds": round(t_setup, 3), "setup_mode": args.setup,
+                   "setup_seconds_other_mode": t_setup_other,
                    "setup_note": "Hierarchy construction (1-D operators, transfers, smoother bounds, "
                                  "coarse eigenbases), outside the timed region",
                    "rhs": "b = 1 (mg_jac.py:59-61)" if rhs == "ones" else

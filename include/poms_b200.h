@@ -234,6 +234,25 @@ int poms_prolong_3d(const double* coarse, double* fine, int n1f, int n2f, int n3
 int poms_dense_matvec(const double* Ainv, const double* x, double* y, int n, void* stream);
 
 /*
+ * Device-side 1-D setup (EXTENSION): the O(n p^2) pieces the reference computes in
+ * Python on the host.  All pointers are device pointers.
+ *  poms_assemble_1d: mass M and stiffness K bands (n, 2p+1) on the knot vector `knots` (n + p + 1
+ *    entries) by Gauss-Legendre quadrature with the p+1 nodes / weights gauss_x, gauss_w on [-1, 1]
+ *    (assembly_1d, sources/matrix_assembler.py:10-77; it computes K and returns only M, Appendix B).
+ *  poms_knot_insertion_rows: rows of the knot-insertion matrix P1 (n_f x n_c) between the nested knot
+ *    vectors Tc, Tf by the Oslo recursion: P1[i, start[i] + w] = coef[i*(p+1) + w]
+ *    (matrix_multi_stages, sources/mg_jac.py:67).
+ *  poms_band_lu_nopiv: LU without row interchanges of an (n, 2q+1) band into dgbtrf storage, row-major
+ *    (3q+1, n) with kl = ku = q (the factor kron_solve_bnd_par takes, sources/kron_product.py:191-197);
+ *    *info_dev = 0, or j+1 when column j has a zero pivot.
+ */
+int poms_assemble_1d(const double* knots, int n, int p, const double* gauss_x, const double* gauss_w,
+                     double* M, double* K, void* stream);
+int poms_knot_insertion_rows(const double* Tc, int nc, const double* Tf, int nf, int p,
+                             int32_t* start, double* coef, void* stream);
+int poms_band_lu_nopiv(const double* band, int n, int q, double* ab, int* info_dev, void* stream);
+
+/*
  * Dense per-axis contraction out[o,i,c] = sum_j Q[i,j] in[o,j,c] on the fp64 tensor cores (DMMA):
  * the 1-D eigenbasis contractions of the fast-diagonalisation coarse solve that replaces
  * splu(csc_matrix(Ac)).solve(rc) (sources/mg_jac.py:98-99; dense Kronecker solve of

@@ -157,7 +157,17 @@ class BandLU:
         q = p
         while q > 0 and not band[:, p - q].any() and not band[:, p + q].any():
             q -= 1
-        lu = cls(*bs.band_lu(band[:, p - q:p + q + 1]), device)
+        from . import setup_device as sd
+        trimmed = band[:, p - q:p + q + 1]
+        if sd.enabled():
+            # device LU without row interchanges (SPD / diagonally dominant bands: mass, GLT); a zero
+            # pivot falls back to LAPACK's pivoting factorisation on the host
+            try:
+                lu = cls(*sd.band_lu(trimmed), device)
+            except np.linalg.LinAlgError:
+                lu = cls(*bs.band_lu(trimmed), device)
+        else:
+            lu = cls(*bs.band_lu(trimmed), device)
         lu.band = band          # kept for the slab-partitioned (SPIKE) solve, dist.py
         return lu
 

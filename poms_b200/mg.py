@@ -154,7 +154,9 @@ class Transfer:
                 self.R.append(None)
                 self.P1_rows.append(None)
                 continue
-            st, cf, _ = bs.knot_insertion_rows(Tc, Tf, p)
+            from . import setup_device as sd
+            rows = sd.knot_insertion_rows if sd.enabled() else bs.knot_insertion_rows
+            st, cf, _ = rows(Tc, Tf, p)
             stt, cft = bs.rows_transpose(st, cf, nc)
             self.P.append(_AxisOp(st, cf, nc, device))
             self.R.append(_AxisOp(stt, cft, nf, device))
@@ -370,7 +372,11 @@ class CoarseSolver:
         for a in range(A.ndim):
             Kd = bs.band_to_dense(A.Ks[a])
             Md = bs.band_to_dense(A.Ms[a])
-            w, Q = eigh(0.5 * (Kd + Kd.T), 0.5 * (Md + Md.T))
+            from . import setup_device as sd
+            if sd.enabled():
+                w, Q = sd.gen_eigh(Kd, Md, device)
+            else:
+                w, Q = eigh(0.5 * (Kd + Kd.T), 0.5 * (Md + Md.T))
             lam.append(w)
             n = Q.shape[0]
             z = np.zeros(n, dtype=np.int32)
@@ -450,6 +456,9 @@ def _gen_eig_max(Kb, Tb):
     solves, tolerance 1e-3 (the top of these spectra is a dense cluster: a tight tolerance took
     256 s at n = 8197, and the Chebyshev interval carries a 10 % safety factor anyway)."""
     n = Kb.shape[0]
+    from . import setup_device as sd
+    if sd.enabled():
+        return sd.gen_eig_max(Kb, Tb)
     if n <= 1500:
         from scipy.linalg import eigh
         return float(eigh(bs.band_to_dense(Kb), bs.band_to_dense(Tb), eigvals_only=True,
@@ -506,7 +515,18 @@ class Hierarchy:
     """
 
     def __init__(self, p, N, ndim=None, Nc=8, device="cuda", smoother="glt", nu=1, ratio=4.0,
-                 safety=1.1, slab=None, lengths=None, min_planes=32, coarsen="semi"):
+                 safety=1.1, slab=None, lengths=None, min_planes=32, coarsen="semi", setup="host"):
+        """setup='device': the 1-D setup (assembly, knot-insertion rows, banded LU, eigenproblems)
+        runs on the GPU (setup_device.py); 'host' (default): NumPy / SciPy."""
+        if setup == "device":
+            from . import setup_device as sd
+            with sd.device_setup(True, device):
+                self.__init__(p, N, ndim=ndim, Nc=Nc, device=device, smoother=smoother, nu=nu, ratio=ratio,
+                              safety=safety, slab=slab, lengths=lengths, min_planes=min_planes,
+                              coarsen=coarsen, setup="host")
+            self.setup = "device"
+            return
+        self.setup = "host"
         if np.isscalar(N):
             N = [int(N)] * int(ndim)
         # domain [0, L_1] x .. x [0, L_d] (default the unit cube).  Weak scaling extends the domain

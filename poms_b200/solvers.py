@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from . import profiling
 from .stencil import (StencilVector, DeviceContext, dot_into, _stream, EPI_STORE, EPI_RESID,
-                      EPI_JACOBI)
+                      EPI_JACOBI, EPI_DINV)
 
 __all__ = ["crl", "pcg", "jacobi", "damped_jacobi", "pcg_glt", "gmres", "rb_jacobi"]
 

@@ -639,7 +639,9 @@ class KronSumMatrix:
         """-Lap(u)+u on the tensor-product space with the given per-axis knot vectors: the
         operator `assembly_2d` builds (/root/reference/sources/matrix_assembler.py:82-179), as
         K(x)M + M(x)(K+M) [2-D] / K(x)M(x)M + M(x)K(x)M + M(x)M(x)(K+M) [3-D]."""
-        MK = [bs.assemble_1d_bands(p, T) for T in knots]
+        from . import setup_device as sd
+        asm = sd.assemble_1d_bands if sd.enabled() else bs.assemble_1d_bands
+        MK = [asm(p, T) for T in knots]
         Ms = [m for m, k in MK]
         Ks = [k for m, k in MK]
         Ks[-1] = Ks[-1] + Ms[-1]
