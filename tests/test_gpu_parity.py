@@ -328,12 +328,16 @@ def test_jacobi_damped_jacobi_crl_golden(dev, golden, tag):
         assert rel(_arr(x2), g["x_damped2"]) < 1e-9
     gd = golden("pcg_diag_" + tag)
     x, info = pcg(S, jacobi, b, tol=float(gd["tol"]), maxiter=int(gd["maxiter"]))
-    assert abs(info["niter"] - int(gd["info"][0])) <= (0 if tag != "p3_ne12" else 1)
-    assert rel(_arr(x), gd["x"]) < 1e-6
+    # identical iteration counts (measured: profiles/r02_diag_iteration_counts_vs_golden.txt) and 1e-10
+    # on x; p3_ne12 is the ill-conditioned run whose history amplifies rounding:
+    # same count, x to 1e-7 (measured 2e-9 / 1e-8)
+    xtol = 1e-10 if tag != "p3_ne12" else 1e-7
+    assert info["niter"] == int(gd["info"][0])
+    assert rel(_arr(x), gd["x"]) < xtol
     gc = golden("crl_" + tag)
     x, info = crl(S, b, tol=1e-5, maxiter=60)
-    assert abs(info["niter"] - int(gc["info"][0])) <= 1
-    assert rel(_arr(x), gc["x"]) < 1e-6
+    assert info["niter"] == int(gc["info"][0])
+    assert rel(_arr(x), gc["x"]) < xtol
     assert set(info) == {"niter", "success", "res_norm"}
 
 
@@ -344,14 +348,16 @@ def test_pcg_glt_golden(dev, golden, tag):
     A, S, V = _golden_problem(g, dev)
     M1, M2 = _mat1d(g["M1"], dev), _mat1d(g["M2"], dev)
     x, info = pcg_glt(S, M1, M2, _vec(V, g["b"]), tol=float(g["tol"]), maxiter=100)
-    assert abs(info["niter"] - int(g["info"][0])) <= (0 if tag == "p1_ne4" else 1)
+    assert info["niter"] == int(g["info"][0])      # identical counts on all four golden runs
     from oracle import poms_oracle as po
     _, io = po.pcg_glt(po.StencilOperator2D(g["A"]), g["M1"], g["M2"], g["b"],
                        tol=float(g["tol"]), maxiter=100)
     ref_rr = io["history"]
     m = min(8, len(ref_rr), len(info["history"]))
     assert np.allclose(info["history"][:m], ref_rr[:m], rtol=1e-9)
-    assert rel(_arr(x), g["x"]) < 1e-5
+    # p3_ne12: the history leaves the reference's after iteration 30 (rounding amplified by the
+    # ill-conditioned run; measured x agreement 1.1e-7), the other runs agree to 1e-15
+    assert rel(_arr(x), g["x"]) < (1e-10 if tag != "p3_ne12" else 1e-6)
 
 
 # ----------------------------------------------------------------------------- a13-a17 two-grid
