@@ -739,6 +739,13 @@ def _graphs_wanted(h, b):
     if not (V.compatible(h.levels[0].V) and V.pads == h.levels[0].V.pads):
         return None
     if V.slab is not None and V.slab.size > 1:
+        # POMS_B200_GRAPH_DIST=1 (experimental): capture the slab iteration too -- the peer-store halo
+        # kernels and the NCCL collectives capture and replay correctly (measured on 2 GPUs: C5 265.7
+        # vs 266.2 ms, C4 332 vs 348 ms), but the processes then hang in NCCL teardown at exit, so the
+        # default stays: eager launches on the persistent vectors
+        if (os.environ.get("POMS_B200_GRAPH_DIST", "0") == "1" and not profiling.enabled()
+                and os.environ.get("POMS_B200_GRAPH", "1") != "0"):
+            return "graph"
         return "persistent"
     if os.environ.get("POMS_B200_GRAPH", "1") != "0" and not profiling.enabled():
         return "graph"
