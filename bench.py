@@ -279,10 +279,18 @@ def main():
     lengths = [float(world) if scaling == "weak" else 1.0] + [1.0] * (ndim - 1)
     # coarsest level: solved exactly by fast diagonalisation, so it need not be tiny; stopping at 32
     # elements per axis in 3-D saves two levels of launch-latency-bound kernels per V-cycle
-    # The same coarsest grid at every GPU count (32 elements per axis per GPU in 3-D): with slabs the
-    # coarsest level is gathered and solved redundantly; its 1-D eigenbasis along the slab axis is
-    # (32 G + p)^2 and is applied by the DMMA contraction kernel, so it stays cheap at 8 GPUs.
-    Nc = args.nc if args.nc > 0 else (32 if ndim == 3 else 8)
+    # Coarsest grid (solved exactly by fast diagonalisation; its dense 1-D eigenbasis contractions run on
+    # the fp64 tensor cores, poms_axis_dense_dmma).  One GPU, 3-D: a quarter of the fine resolution per
+    # axis, at most 128 elements (C5: 131^3 unknowns, 3 levels; measured 246 ms vs 259 ms with 64 and
+    # 262 ms with 32 elements, profiles/r02_bench_c5_nc*.json).  With slabs the coarsest level is gathered
+    # and solved redundantly on every GPU, so it stays at 32 elements per axis per GPU (5 levels at
+    # every N > 1; its slab-axis eigenbasis is (32 G + p)^2).  --nc forces one value for every N.
+    if args.nc > 0:
+        Nc = args.nc
+    elif ndim == 3:
+        Nc = max(32, min(128, N // 4)) if world == 1 else 32
+    else:
+        Nc = 8
     t_setup = time.perf_counter()
     h = Hierarchy(p, Ns, device=dev, smoother=args.smoother, nu=args.nu, slab=slab,
                   lengths=lengths, Nc=Nc, coarsen="uniform", setup=args.setup)
@@ -522,7 +530,9 @@ def main():
         # the CPU port has the two GLT smoothers only
         smo = "glt" if args.smoother == "jacobi" else args.smoother
         try:
-            dofc, dtc, infoc, cores, label = cpu_port_solve(ndim, p, Ns_cpu, smoother=smo, Nc=Nc)
+            # the CPU port inverts its coarsest operator densely: its coarsest grid stays small
+            # (same rule as --impl reference: 8 elements per axis)
+            dofc, dtc, infoc, cores, label = cpu_port_solve(ndim, p, Ns_cpu, smoother=smo, Nc=8)
             line["cpu_baseline"] = {
                 "value": dofc / dtc, "unit": "DOF/s", "cores": cores, "kind": "port",
                 "host_cores_available": os.cpu_count(),
