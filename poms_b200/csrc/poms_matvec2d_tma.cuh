@@ -135,7 +135,9 @@ kron_matvec2d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_
                 const bool have = j < jv1;
                 const int i1 = j - P;
                 const bool emit = i1 >= c_lo;
-                // epilogue operands of the output row, requested before the arithmetic
+                // epilogue operands of the output row, requested before the arithmetic (a register
+                // pipeline two rows deep was measured: SLOWER under the 128-register cap, C4 residual
+                // 0.655 vs 0.551 ms; ncu still shows these loads exposed: long_scoreboard 3.0 per issue)
                 double b0 = 0.0, b1 = 0.0, x0 = 0.0, x1 = 0.0;
                 if (emit) {
                     if (need_b) {
