@@ -108,7 +108,7 @@ def pin_cpu_threads():
     return n
 
 
-def cpu_port_solve(ndim, p, N, tol=1e-10, smoother="glt", Nc=8):
+def cpu_port_solve(ndim, p, N, tol=1e-10, smoother="glt", Nc=8, ratio=4.0):
     """One MG-PCG solve with the CPU port of the same algorithm: oracle/poms_oracle_mt.py (numba,
     all host threads), or the single-threaded NumPy oracle if numba is unavailable.  b = A x0 like
     the GPU arm.  Returns (dof, seconds, info, cores, label)."""
@@ -125,7 +125,7 @@ def cpu_port_solve(ndim, p, N, tol=1e-10, smoother="glt", Nc=8):
             _cpu_port.update(mod=po, cls=po.MGHierarchy, cores=1,
                              label="NumPy/SciPy oracle, single thread (numba unavailable: %s)" % exc)
     # same hierarchy rule as the GPU arm: uniform coarsening down to Nc elements per axis
-    h = _cpu_port["cls"](p, [N] * ndim, smoother=smoother, nu=1, Nc=Nc, coarsen="uniform")
+    h = _cpu_port["cls"](p, [N] * ndim, smoother=smoother, nu=1, Nc=Nc, coarsen="uniform", ratio=ratio)
     A = h.levels[0]["A"]
     x0 = np.zeros(A.npts)
     for a in range(ndim):
@@ -190,7 +190,7 @@ def run_reference(args, rank):
     vals = []
     t_all = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        dof, dt, info, cores, label = cpu_port_solve(ndim, p, Ns,
+        dof, dt, info, cores, label = cpu_port_solve(ndim, p, Ns, ratio=args.ratio,
                                                      smoother=resolve_smoother(args.smoother, p))
         if i >= args.warmup:
             vals.append(dof / dt)
@@ -228,6 +228,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--smoother", default="auto", choices=["auto", "glt", "glt_poly", "jacobi"])
     ap.add_argument("--nu", type=int, default=1)
+    ap.add_argument("--ratio", type=float, default=6.0,
+                    help="smoothing interval [lmax/ratio, lmax] of the Richardson / Chebyshev smoother "
+                         "(step 1/theta, theta = (lmax + lmin)/2).  Measured on C5: ratio 2.5 / 3 / 4 / 6 / 10 "
+                         "-> 22 / 21 / 21 / 20 / 20 iterations, 258 / 247 / 246 / 236 / 237 ms "
+                         "(profiles/r02_bench_c5_ratio*.json); both arms use the same value")
     ap.add_argument("--nc", type=int, default=0, help="coarsest grid (elements per axis); 0 = auto")
     ap.add_argument("--rhs", default="auto", choices=["auto", "ones", "manufactured"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -293,7 +298,7 @@ def main():
         Nc = 8
     t_setup = time.perf_counter()
     h = Hierarchy(p, Ns, device=dev, smoother=args.smoother, nu=args.nu, slab=slab,
-                  lengths=lengths, Nc=Nc, coarsen="uniform", setup=args.setup)
+                  lengths=lengths, Nc=Nc, coarsen="uniform", setup=args.setup, ratio=args.ratio)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
     t_setup_other = None
@@ -423,7 +428,7 @@ def main():
     if args.smoother == "glt_poly" and world == 1 and not args.no_exact_glt:
         try:
             hg = Hierarchy(p, Ns, device=dev, smoother="glt", nu=args.nu, slab=slab, lengths=lengths,
-                           Nc=Nc, coarsen="uniform")
+                           Nc=Nc, coarsen="uniform", ratio=args.ratio)
             xg, infog = mg_pcg(hg, b, tol=1e-10, maxiter=200)
             barrier()
             ng = min(args.steps, 3)
@@ -491,8 +496,8 @@ def main():
                                         else " split into %d slabs along axis 1" % world) if world > 1
                                        else ""),
                    "ndim": ndim, "p": p, "elements": Ns, "dof": dof_global, "domain": lengths,
-                   "solver": "pcg + V(%d,%d) %s-Chebyshev multigrid, tol 1e-10 relative"
-                             % (args.nu, args.nu, args.smoother),
+                   "solver": "pcg + V(%d,%d) %s-Chebyshev multigrid (smoothing interval lmax/%g .. lmax), "
+                             "tol 1e-10 relative" % (args.nu, args.nu, args.smoother, args.ratio),
                    "smoother_note": ("glt_poly = degree-3 polynomial approximation of the reference's GLT "
                                      "Kronecker solve, an EXTENSION (DESIGN.md section 3); `exact_glt` "
                                      "carries the same solve with the reference's exact GLT smoother")
@@ -532,7 +537,8 @@ def main():
         try:
             # the CPU port inverts its coarsest operator densely: its coarsest grid stays small
             # (same rule as --impl reference: 8 elements per axis)
-            dofc, dtc, infoc, cores, label = cpu_port_solve(ndim, p, Ns_cpu, smoother=smo, Nc=8)
+            dofc, dtc, infoc, cores, label = cpu_port_solve(ndim, p, Ns_cpu, smoother=smo, Nc=8,
+                                                            ratio=args.ratio)
             line["cpu_baseline"] = {
                 "value": dofc / dtc, "unit": "DOF/s", "cores": cores, "kind": "port",
                 "host_cores_available": os.cpu_count(),
