@@ -33,6 +33,33 @@ def block_bounds(n, size, rank):
     return s, e
 
 
+def p2p_offsets(n_glob, size, rank, w):
+    """Plane offsets of a peer-store halo exchange of width `w` (host logic of `Slab._exchange_p2p`,
+    pure so that it can be tested without a GPU).  Every rank stores [glo ghost | n_own owned | ghi
+    ghost] planes with glo = w except on rank 0 and ghi = w except on the last rank.  Returns the
+    plane index (in the rank's own storage) of the w owned planes it pushes to the lower / upper
+    neighbour (`src_lo`, `src_hi`) and the plane index IN THE NEIGHBOUR'S storage where they land
+    (`dst_lo`: the lower neighbour's upper ghost planes, `dst_hi`: the upper neighbour's lower ghost
+    planes); None where there is no neighbour."""
+    s, e = block_bounds(n_glob, size, rank)
+    n_own = e - s + 1
+    glo = w if rank > 0 else 0
+    ghi = w if rank < size - 1 else 0
+    out = {"n_own": n_own, "glo": glo, "ghi": ghi, "src_lo": None, "dst_lo": None, "src_hi": None,
+           "dst_hi": None}
+    if rank > 0:
+        assert n_own >= w
+        s_, e_ = block_bounds(n_glob, size, rank - 1)
+        glo_nb = w if rank - 1 > 0 else 0
+        out["src_lo"] = glo
+        out["dst_lo"] = glo_nb + (e_ - s_ + 1)
+    if rank < size - 1:
+        assert n_own >= w
+        out["src_hi"] = glo + n_own - w
+        out["dst_hi"] = 0
+    return out
+
+
 class _DeviceBlob:
     """A raw device allocation exposed through __cuda_array_interface__ so that torch can view it
     (torch.as_tensor) without owning it."""
@@ -233,25 +260,21 @@ class Slab:
         V = v.space
         a = self.arena
         w = V.pads[0]
-        n_own = V.local_shape[0]
         per = int(np.prod(V.pitched_shape[1:]))              # doubles per plane
         i, off = v._arena_key
         ch, fl = a.chunks[i], a.chunks[0]
         base = v._buf.data_ptr()
         assert base == ch["base"] + off
-        n_glob = V.npts[0]
+        o = p2p_offsets(V.npts[0], self.size, self.rank, w)
+        assert o["n_own"] == V.local_shape[0] and o["glo"] == V.glo and o["ghi"] == V.ghi
         src_lo = dst_lo = src_hi = dst_hi = lo_f = hi_f = None
-        if self.rank > 0:
-            assert V.glo == w and n_own >= w
-            s_, e_ = block_bounds(n_glob, self.size, self.rank - 1)
-            glo_nb = w if self.rank - 1 > 0 else 0
-            src_lo = base + 8 * per * V.glo
-            dst_lo = ch["lo"] + off + 8 * per * (glo_nb + (e_ - s_ + 1))   # its upper ghost planes
+        if o["src_lo"] is not None:
+            src_lo = base + 8 * per * o["src_lo"]
+            dst_lo = ch["lo"] + off + 8 * per * o["dst_lo"]              # its upper ghost planes
             lo_f = fl["lo"]
-        if self.rank < self.size - 1:
-            assert V.ghi == w and n_own >= w
-            src_hi = base + 8 * per * (V.glo + n_own - w)
-            dst_hi = ch["hi"] + off                                         # its lower ghost planes
+        if o["src_hi"] is not None:
+            src_hi = base + 8 * per * o["src_hi"]
+            dst_hi = ch["hi"] + off + 8 * per * o["dst_hi"]              # its lower ghost planes
             hi_f = fl["hi"]
         with profiling.region("halo_exchange", 2 * 8 * w * per):
             _lib.check(a.L.poms_halo_exchange_p2p(src_lo, dst_lo, src_hi, dst_hi, w * per, fl["base"],

@@ -128,3 +128,28 @@ def test_spike_partitioned_solve(p, q, n, G):
     assert np.abs(x - xr).max() < 1e-13 * np.abs(xr).max()
     # truncated spikes: the correction only touches planes near the interfaces
     assert max(st.mW) <= 60 and max(st.mV) <= 60
+
+
+def test_peer_store_halo_offsets_reproduce_a_ghost_update():
+    """Host logic of the peer-store halo exchange (dist.p2p_offsets): emulate the pushes of every rank
+    on NumPy slabs of an uneven partition and compare the ghost planes with the global array."""
+    import numpy as np
+    from poms_b200.dist import p2p_offsets, block_bounds
+    for n_glob, size, w in ((37, 4, 3), (515, 8, 4), (16, 2, 1), (131, 3, 2)):
+        G = np.arange(n_glob * 5, dtype=float).reshape(n_glob, 5)
+        offs = [p2p_offsets(n_glob, size, r, w) for r in range(size)]
+        slabs = []
+        for r, o in enumerate(offs):
+            s, e = block_bounds(n_glob, size, r)
+            buf = np.full((o["glo"] + o["n_own"] + o["ghi"], 5), np.nan)
+            buf[o["glo"]:o["glo"] + o["n_own"]] = G[s:e + 1]
+            slabs.append(buf)
+        for r, o in enumerate(offs):                      # every rank pushes to its neighbours
+            if o["src_lo"] is not None:
+                slabs[r - 1][o["dst_lo"]:o["dst_lo"] + w] = slabs[r][o["src_lo"]:o["src_lo"] + w]
+            if o["src_hi"] is not None:
+                slabs[r + 1][o["dst_hi"]:o["dst_hi"] + w] = slabs[r][o["src_hi"]:o["src_hi"] + w]
+        for r, o in enumerate(offs):
+            s, e = block_bounds(n_glob, size, r)
+            want = G[s - o["glo"]:e + 1 + o["ghi"]]
+            assert np.array_equal(slabs[r], want), (n_glob, size, w, r)
