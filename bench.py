@@ -530,7 +530,7 @@ def main():
         k = kern[mv_name]
         line["kron_matvec"] = {"achieved_gbs": k["gbs"], "frac_of_peak": k["gbs"] / peak,
                                "launches": k["launches"]}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
         Ns_cpu = min(N, cpu_sample_size(ndim))
         # the CPU port has the two GLT smoothers only
         smo = "glt" if args.smoother == "jacobi" else args.smoother
