@@ -172,8 +172,8 @@ extern "C" int poms_halo_exchange_p2p(const double* src_lo, double* dst_lo, cons
 // splu(csc_matrix(Ac)).solve(rc) (/root/reference/sources/mg_jac.py:98-99) and the dense
 // Kronecker solve of /root/reference/sources/kron_product.py:93-117.  A/B partner of
 // poms_axis_gather with W = n_in (scalar FMA, one coefficient load per FMA).
-// CTA = 4 warps, tile 32 (i) x 64 (c) with K chunks of 32 staged in shared memory; a warp owns
-// 8 rows x 64 columns = 8 accumulator fragments.  TRANS: the contraction runs along the
+// CTA = 4 warps, tile 64 (i) x 64 (c) with K chunks of 32 staged in shared memory; a warp owns
+// 16 rows x 64 columns = 16 accumulator fragments.  TRANS: the contraction runs along the
 // CONTIGUOUS axis (n_inner == 1): the "column" index is then the outer index o.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
@@ -186,7 +186,9 @@ template <bool TRANS>
 __global__ void __launch_bounds__(128) axis_dense_dmma_kernel(
     const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ Q, int n_in, int n_out,
     int64_t so_in, int64_t sa_in, int64_t so_out, int64_t sa_out, int64_t n_cols) {
-    constexpr int TM = 32, TN = 64, TK = 32, QP = TK + 4, XP = TN + 8;
+    // CTA tile 64 (i) x 64 (c); a warp owns 16 rows x 64 columns = 2 x 8 accumulator fragments, so every
+    // B fragment feeds two DMMAs (10 shared loads per 16 DMMAs; the 32-row version needed 9 per 8)
+    constexpr int TM = 64, TN = 64, TK = 32, QP = TK + 4, XP = TN + 8;
     __shared__ double Qs[TM][QP];     // Q[i0 + r][k0 + k]
     __shared__ double Xs[TK][XP];     // X[k0 + k][c0 + c]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -195,11 +197,12 @@ __global__ void __launch_bounds__(128) axis_dense_dmma_kernel(
     const int64_t o = TRANS ? 0 : blockIdx.z;
     const double* inb = in + o * so_in;
     double* outb = out + o * so_out;
-    double acc[8][2];
+    double acc[2][8][2];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = 0.0;
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[h][t][0] = acc[h][t][1] = 0.0;
     for (int k0 = 0; k0 < n_in; k0 += TK) {
-        // stage Q tile (coalesced along k) and X tile
         for (int e = tid; e < TM * TK; e += 128) {
             const int r = e / TK, k = e - r * TK;
             const int i = i0 + r, j = k0 + k;
@@ -223,25 +226,30 @@ __global__ void __launch_bounds__(128) axis_dense_dmma_kernel(
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < TK; kk += 4) {
-            const double a = Qs[warp * 8 + (lane >> 2)][kk + (lane & 3)];
+            const double a0 = Qs[warp * 16 + (lane >> 2)][kk + (lane & 3)];
+            const double a1 = Qs[warp * 16 + 8 + (lane >> 2)][kk + (lane & 3)];
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 const double b = Xs[kk + (lane & 3)][t * 8 + (lane >> 2)];
-                dmma8x8x4(acc[t][0], acc[t][1], a, b);
+                dmma8x8x4(acc[0][t][0], acc[0][t][1], a0, b);
+                dmma8x8x4(acc[1][t][0], acc[1][t][1], a1, b);
             }
         }
         __syncthreads();
     }
-    const int i = i0 + warp * 8 + (lane >> 2);
-    if (i < n_out) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
+    for (int h2 = 0; h2 < 2; ++h2) {
+        const int i = i0 + warp * 16 + 8 * h2 + (lane >> 2);
+        if (i < n_out) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int64_t cc = c0 + t * 8 + 2 * (lane & 3) + h;
-                if (cc < n_cols) {
-                    if (!TRANS) outb[(int64_t)i * sa_out + cc] = acc[t][h];
-                    else out[cc * so_out + i] = acc[t][h];
+            for (int t = 0; t < 8; ++t) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t cc = c0 + t * 8 + 2 * (lane & 3) + h;
+                    if (cc < n_cols) {
+                        if (!TRANS) outb[(int64_t)i * sa_out + cc] = acc[h2][t][h];
+                        else out[cc * so_out + i] = acc[h2][t][h];
+                    }
                 }
             }
         }
@@ -257,11 +265,11 @@ extern "C" int poms_axis_dense_dmma(const double* in, double* out, const double*
     if (n_inner == 1) {
         // contraction along the contiguous axis: columns = the n_outer lines
         if (sa_in != 1 || sa_out != 1) return x_bad_arg(8, "contiguous axis needs unit stride");
-        dim3 grid((unsigned)((n_outer + 63) / 64), (unsigned)((n_out + 31) / 32), 1);
+        dim3 grid((unsigned)((n_outer + 63) / 64), (unsigned)((n_out + 63) / 64), 1);
         axis_dense_dmma_kernel<true><<<grid, 128, 0, st>>>(in, out, Q, n_in, n_out, so_in, 1, so_out, 1, n_outer);
     } else {
         if (n_outer > 65535) return x_bad_arg(6, "n_outer");
-        dim3 grid((unsigned)((n_inner + 63) / 64), (unsigned)((n_out + 31) / 32), (unsigned)n_outer);
+        dim3 grid((unsigned)((n_inner + 63) / 64), (unsigned)((n_out + 63) / 64), (unsigned)n_outer);
         axis_dense_dmma_kernel<false><<<grid, 128, 0, st>>>(in, out, Q, n_in, n_out, so_in, sa_in, so_out,
                                                            sa_out, n_inner);
     }
