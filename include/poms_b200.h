@@ -94,6 +94,20 @@ int poms_kron_matvec_3d_ex(const double* x, double* y, const double* b,
                            const double* m3, const double* k3,
                            int epilogue, double omega, double* dot_out, void* ws, void* stream,
                            const double* toep_host, const int* toep_rng_host);
+/* poms_kron_matvec_3d_ex with a fused dot product against a THIRD vector: with POMS_EPI_AXPY and
+ * dot_with != NULL the reduction written to *dot_out is sum y[i] * dot_with[i] (y = the epilogue's
+ * output) instead of sum (om*v)^2 -- the s.r of the CG drivers (sources/solvers.py:117-118) computed by the
+ * last smoother pass.  dot_with has the layout of x (same ghost planes).  *fused_host = 1 when the TMA
+ * kernel did it, 0 when the launch fell back to a kernel without this epilogue (*dot_out then holds the
+ * standard reduction and the caller computes the dot product itself). */
+int poms_kron_matvec_3d_dotv(const double* x, double* y, const double* b,
+                             int n1, int n2, int n3, int64_t ld, int64_t pld, int glo, int ghi,
+                             int p, int form,
+                             const double* m1, const double* k1, const double* m2, const double* k2,
+                             const double* m3, const double* k3,
+                             int epilogue, double omega, double* dot_out, void* ws, void* stream,
+                             const double* toep_host, const int* toep_rng_host,
+                             const double* dot_with, int* fused_host);
 void poms_set_force_generic(int flag);
 /* A/B timing only: fix the axis-1 chunk (planes per CTA) of the 3-D mat-vec; 0 = automatic. */
 void poms_set_matvec3d_chunk(int chunk);

@@ -24,6 +24,9 @@ _PROTOS = {
     "poms_kron_matvec_3d_ex": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _i,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp,
                                         _vp, _vp]),
+    "poms_kron_matvec_3d_dotv": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _i,
+                                          _vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp,
+                                          _vp, _vp, _vp, C.POINTER(C.c_int)]),
     "poms_set_force_generic": (None, [_i]),
     "poms_set_matvec3d_chunk": (None, [_i]),
     "poms_set_matvec3d_variant": (None, [_i]),

@@ -486,6 +486,15 @@ extern "C" int poms_kron_matvec_3d(const double* x, double* y, const double* b, 
 static int g_force_generic = 0;
 extern "C" void poms_set_force_generic(int flag) { g_force_generic = flag; }
 
+extern "C" int poms_kron_matvec_3d_dotv(const double* x, double* y, const double* b, int n1, int n2,
+                                        int n3, int64_t ld, int64_t pld, int glo, int ghi, int p,
+                                        int form, const double* m1, const double* k1,
+                                        const double* m2, const double* k2, const double* m3,
+                                        const double* k3, int epilogue, double omega,
+                                        double* dot_out, void* ws, void* stream,
+                                        const double* toep_host, const int* toep_rng_host,
+                                        const double* dot_with, int* fused_host);
+
 extern "C" int poms_kron_matvec_3d_ex(const double* x, double* y, const double* b, int n1, int n2,
                                       int n3, int64_t ld, int64_t pld, int glo, int ghi, int p,
                                       int form, const double* m1, const double* k1,
@@ -493,6 +502,20 @@ extern "C" int poms_kron_matvec_3d_ex(const double* x, double* y, const double* 
                                       const double* k3, int epilogue, double omega,
                                       double* dot_out, void* ws, void* stream,
                                       const double* toep_host, const int* toep_rng_host) {
+    return poms_kron_matvec_3d_dotv(x, y, b, n1, n2, n3, ld, pld, glo, ghi, p, form, m1, k1, m2, k2, m3, k3,
+                                    epilogue, omega, dot_out, ws, stream, toep_host, toep_rng_host, nullptr,
+                                    nullptr);
+}
+
+extern "C" int poms_kron_matvec_3d_dotv(const double* x, double* y, const double* b, int n1, int n2,
+                                        int n3, int64_t ld, int64_t pld, int glo, int ghi, int p,
+                                        int form, const double* m1, const double* k1,
+                                        const double* m2, const double* k2, const double* m3,
+                                        const double* k3, int epilogue, double omega,
+                                        double* dot_out, void* ws, void* stream,
+                                        const double* toep_host, const int* toep_rng_host,
+                                        const double* dot_with, int* fused_host) {
+    if (fused_host) *fused_host = 0;
     if (!x) return bad_arg(1, "x");
     if (!y) return bad_arg(2, "y");
     if (epilogue != POMS_EPI_STORE && epilogue != POMS_EPI_AXPY && !b) return bad_arg(3, "b required by epilogue");
@@ -509,7 +532,7 @@ extern "C" int poms_kron_matvec_3d_ex(const double* x, double* y, const double* 
     if (!g_force_generic) {
         // fast path: TMA-staged pipeline (needs 16-byte aligned rows); 1 = not applicable
         const int trc = try_matvec3d_tma(a, p, form, epilogue, toep_host, toep_rng_host,
-                                         (cudaStream_t)stream);
+                                         (cudaStream_t)stream, dot_with, fused_host);
         if (trc == 0) {
             CHECK_LAUNCH("poms_kron_matvec_3d(tma)");
             return 0;

@@ -543,7 +543,8 @@ static int mv3_variant() {
 // returns 0 on success, 1 if the TMA path does not apply (caller falls back to the generic kernel),
 // other values are errors
 static int try_matvec3d_tma(const MV3& a0, int p, int form, int epilogue, const double* toep, const int* toep_rng,
-                            cudaStream_t st) {
+                            cudaStream_t st, const double* dot_with = nullptr, int* fused = nullptr) {
+    if (fused) *fused = 0;
     if (((uintptr_t)a0.x & 15) || (a0.ld & 1) || (a0.pld & 1)) return 1;
     if (a0.n3 < 8 || a0.n2 < 4) return 1;  // tiny grids: generic kernel
     PFN_encodeTiled enc = get_encode_tiled();
@@ -599,7 +600,8 @@ static int try_matvec3d_tma(const MV3& a0, int p, int form, int epilogue, const 
             }
         }
         const bool need_b = epilogue != POMS_EPI_STORE && a0.b != nullptr;
-        const bool need_x = (epilogue == POMS_EPI_STORE && a0.dot_out) || epilogue == POMS_EPI_JACOBI;
+        const bool dotz = epilogue == POMS_EPI_AXPY && dot_with && a0.dot_out && !((uintptr_t)dot_with & 15);
+        const bool need_x = (epilogue == POMS_EPI_STORE && a0.dot_out) || epilogue == POMS_EPI_JACOBI || dotz;
         if (!sym || (need_b && ((uintptr_t)a0.b & 15))) {
             var = 0;
         } else {
@@ -616,10 +618,15 @@ static int try_matvec3d_tma(const MV3& a0, int p, int form, int epilogue, const 
                 ++ntiles;
             }
             if (need_x) {
-                if (get_tmap(enc, a0.x - (int64_t)a0.glo * a0.pld, a0.n3, a0.n2, a0.n1 + a0.glo + a0.ghi, a0.ld,
+                const double* xt = dotz ? dot_with : a0.x;       // same slab layout (ghost planes) as x
+                if (get_tmap(enc, xt - (int64_t)a0.glo * a0.pld, a0.n3, a0.n2, a0.n1 + a0.glo + a0.ghi, a0.ld,
                              a0.pld, 64 + 2 * sh, 16, &tm3[2]))
                     return 1;
                 ++ntiles;
+            }
+            if (dotz) {
+                g.dot_add = 1;
+                if (fused) *fused = 1;
             }
         }
     }

@@ -50,7 +50,11 @@ kron_matvec3d_v3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
     const MV3& a = g.a;
     constexpr bool NEED_B = (EPI != POMS_EPI_STORE);
     const bool need_b = NEED_B && a.b != nullptr;   // AXPY without b: y = omega*v (zero initial guess)
-    const bool need_x = (EPI == POMS_EPI_STORE && a.dot_out) || EPI == POMS_EPI_JACOBI;
+    // g.dot_add (AXPY epilogue only): the fused reduction is sum y_out * z instead of sum (omega v)^2,
+    // with z delivered through the x-tile ring (tmx is then a map of z): s.r of the CG driver rides in
+    // the last smoother pass (/root/reference/sources/solvers.py:117-118)
+    const bool dotz = (EPI == POMS_EPI_AXPY) && g.dot_add != 0;
+    const bool need_x = (EPI == POMS_EPI_STORE && a.dot_out) || EPI == POMS_EPI_JACOBI || dotz;
     const bool need_t = need_b || need_x;
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -349,8 +353,9 @@ kron_matvec3d_v3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
             dsum = fma(rr, rr, dsum);
         } else if (EPI == POMS_EPI_AXPY) {
             const double w_ = a.omega * v;
-            yp[(int64_t)e * a.ld] = need_b ? bv + w_ : w_;
-            dsum = fma(w_, w_, dsum);
+            const double yo = need_b ? bv + w_ : w_;
+            yp[(int64_t)e * a.ld] = yo;
+            dsum = dotz ? fma(yo, xv, dsum) : fma(w_, w_, dsum);
         } else {
             const double dg = TWO ? dg1 * dA[e] + dg2 * dB[e] : dg1 * dA[e];
             const double dr = a.omega * (bv - v) / dg;

@@ -639,7 +639,10 @@ class Hierarchy:
         return lam
 
     # ---- smoothing: nu Chebyshev steps on B^-1 A --------------------------------------------
-    def smooth(self, lv, b, x, zero_guess):
+    def smooth(self, lv, b, x, zero_guess, final_dot=None):
+        """final_dot = (vector r, device scalar pointer): ask the LAST pass of the smoother to leave
+        x . r in the scalar (fused epilogue of the polynomial smoother); returns (x, fused)."""
+        self._dot_fused = False
         A = lv.A
         V = lv.V
         L = _lib.lib()
@@ -662,8 +665,12 @@ class Hierarchy:
                 # in place: the epilogue reads x[i] and writes x[i] from the same thread, and the
                 # mat-vec input is t1, so no other thread reads x.  Zero guess: x = (1/theta) S2 t1,
                 # x is neither cleared nor read (b = None).
-                lv.S2.apply(t1, x, EPI_AXPY, b=None if (k == 0 and zero_guess) else x,
-                            omega=1.0 / theta)
+                last = final_dot is not None and k == self.nu - 1
+                fused = lv.S2.apply(t1, x, EPI_AXPY, b=None if (k == 0 and zero_guess) else x,
+                                    omega=1.0 / theta, dot_ptr=final_dot[1] if last else None,
+                                    dot_with=final_dot[0] if last else None)
+                if last:
+                    self._dot_fused = bool(fused)
             return x
         if self.smoother == "glt" and self.nu == 1 and all(lu.nopiv for lu in lv.glt_lu):
             # one step: x <- x + (1/theta) B^-1 (b - A x); the update is fused into the last line
@@ -704,9 +711,12 @@ class Hierarchy:
         return x
 
 
-def vcycle(h, l, b):
+def vcycle(h, l, b, final_dot=None):
     """One V(nu,nu) cycle from a zero initial guess on level l.  Returns the level's persistent
-    solution vector `lv.ws("x")`: it is overwritten by the next cycle, copy it to keep it."""
+    solution vector `lv.ws("x")`: it is overwritten by the next cycle, copy it to keep it.
+    final_dot = (r, scalar pointer): the post-smoother's last pass also leaves x . r there when it
+    can (`h._dot_fused` tells)."""
+    h._dot_fused = False
     lv = h.levels[l]
     if l == len(h.levels) - 1:
         return h.coarse.solve(b, out=lv.ws("x"))
@@ -724,7 +734,7 @@ def vcycle(h, l, b):
     ec = vcycle(h, l + 1, rc)
     with profiling.region("prolong_add", 16 * lv.V.local_size, launches=h.ndim):
         lv.transfer.prolong_add(ec, x)
-    h.smooth(lv, b, x, False)
+    h.smooth(lv, b, x, False, final_dot=final_dot)
     return x
 
 
@@ -825,9 +835,17 @@ class _PcgGraphs:
         from .solvers import _reduce
         ctx, L = self.ctx, _lib.lib()
         V = self.x.space
-        s = vcycle(self.h, 0, self.r)
-        with profiling.region("dot", 16 * self.x.n_owned):
-            dot_into(s, self.r, ctx.sptr(self.S_NEW), ctx)
+        # s.r (sources/solvers.py:117-118) can ride in the last smoother pass (POMS_B200_FUSE_SR=1):
+        # measured on C5 it does NOT pay yet -- the extra tile ring of r pushes the p = 4 smoother
+        # pass from two CTAs per SM to one (117.6 KB of shared memory), which costs more than the
+        # 6.5 ms dot kernel it removes (236.9 vs 233.1 ms per solve) -- so the default keeps the
+        # separate dot kernel
+        import os
+        fd = (self.r, ctx.sptr(self.S_NEW)) if os.environ.get("POMS_B200_FUSE_SR") == "1" else None
+        s = vcycle(self.h, 0, self.r, final_dot=fd)
+        if not self.h._dot_fused:
+            with profiling.region("dot", 16 * self.x.n_owned):
+                dot_into(s, self.r, ctx.sptr(self.S_NEW), ctx)
         _reduce(ctx, V, self.S_NEW)
         with profiling.region("p_update", 24 * self.x.n_owned):
             _lib.check(L.poms_p_update(self.p.ptr, s.ptr, self.p.n_owned, ctx.sptr(self.S_NEW),

@@ -690,9 +690,12 @@ class KronSumMatrix:
             self._dev[key] = (m, k)
         return self._dev[key]
 
-    def apply(self, x, y, epi=EPI_STORE, b=None, omega=0.0, dot_ptr=None):
-        """y = epilogue(A x) in one fused pass; optional fused reduction into *dot_ptr."""
+    def apply(self, x, y, epi=EPI_STORE, b=None, omega=0.0, dot_ptr=None, dot_with=None):
+        """y = epilogue(A x) in one fused pass; optional fused reduction into *dot_ptr.
+        dot_with (3-D, EPI_AXPY): request *dot_ptr = y . dot_with instead of the epilogue's own
+        reduction; returns True when the kernel did it (False: the caller computes the dot)."""
         V = x.space
+        self._fused_dot = False
         assert V.npts == self.npts, (V.npts, self.npts)
         ctx = DeviceContext.get(V.device)
         m, k = self._bands(V)
@@ -724,10 +727,11 @@ class KronSumMatrix:
             return
         if slab is not None:
             slab.exchange(x)
-        with profiling.region("kron_matvec_%dd" % self.ndim, nbytes):
-            self._launch(L, V, x, y, bp, m, kp, epi, omega, dot_ptr, ctx)
+        with profiling.region("kron_matvec_%dd" % self.ndim, nbytes + (8 * V.local_size if dot_with is not None else 0)):
+            self._launch(L, V, x, y, bp, m, kp, epi, omega, dot_ptr, ctx, dot_with=dot_with)
+        return self._fused_dot
 
-    def _launch(self, L, V, x, y, bp, m, kp, epi, omega, dot_ptr, ctx, z0=0, z1=None):
+    def _launch(self, L, V, x, y, bp, m, kp, epi, omega, dot_ptr, ctx, z0=0, z1=None, dot_with=None):
         """One kernel launch for the output planes [z0, z1) of the slab (default: all of them).  A
         sub-range is the same kernel on shifted pointers: the planes outside it are ghost planes of
         the sub-problem (glo + z0 below, ghi + n1 - z1 above)."""
@@ -753,13 +757,17 @@ class KronSumMatrix:
             rng[1] = max(int(rng[0]), min(z1 - z0, int(rng[1]) - V.starts[0] - z0))
             W = 2 * self.P + 1
             off = 8 * z0 * x.pld                        # bytes from plane 0 to plane z0
-            _lib.check(L.poms_kron_matvec_3d_ex(
+            import ctypes
+            fused = ctypes.c_int(0)
+            _lib.check(L.poms_kron_matvec_3d_dotv(
                 x.ptr + off, y.ptr + off, bp + off if bp is not None else None, z1 - z0, n2, n3,
                 x.ld, x.pld, V.glo + z0, V.ghi + n1 - z1, self.P, self.form,
                 m[0].data_ptr() + 8 * z0 * W, kp[0] + 8 * z0 * W if kp[0] is not None else None,
                 m[1].data_ptr(), kp[1], m[2].data_ptr(), kp[2], epi,
-                float(omega), dot_ptr, ctx.ws_ptr, _stream(), coef.ctypes.data, rng.ctypes.data),
-                "poms_kron_matvec_3d_ex")
+                float(omega), dot_ptr, ctx.ws_ptr, _stream(), coef.ctypes.data, rng.ctypes.data,
+                dot_with.ptr + off if dot_with is not None else None, ctypes.byref(fused)),
+                "poms_kron_matvec_3d_dotv")
+            self._fused_dot = bool(fused.value)
 
     def dot(self, v):
         out = StencilVector(v.space, zero=False)

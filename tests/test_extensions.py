@@ -139,3 +139,33 @@ def test_full_3d_stencil_matvec_and_solver(dev, p, N):
     xo, io = po.pcg(So, po.jacobi, So.dot(xt), tol=1e-8, maxiter=200)
     assert info["niter"] == io["niter"]
     assert np.abs(xs.toarray().reshape(xo.shape) - xo).max() < 1e-9 * np.abs(xo).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p,N", [(3, (40, 30, 70)), (2, (20, 33, 129))])
+def test_axpy_epilogue_with_fused_dot_against_a_third_vector(dev, p, N):
+    """EPI_AXPY with dot_with = z: y = b + om * (S x) and the fused reduction y . z (the s.r of the CG
+    driver riding in the last smoother pass), on grids with interior, boundary and ragged tiles."""
+    import torch
+    from poms_b200 import bsplines as bs
+    from poms_b200.stencil import (StencilVector, StencilVectorSpace, KronSumMatrix, DeviceContext, EPI_AXPY)
+    npts = [n + p for n in N]
+    glt = [bs.glt_band(p, n, degree=max(2 * p - 1, 1)) for n in npts]
+    S2 = KronSumMatrix([bs.poly_inverse_factors(b_, 3)[1] for b_ in glt])
+    V = StencilVectorSpace(npts, [S2.P] * 3, [False] * 3, device=dev)
+    rng = np.random.default_rng(7)
+    X, B, Z = (rng.standard_normal(npts) for _ in range(3))
+    x, b, z, y = (StencilVector.from_array(V, a) for a in (X, B, Z, np.zeros(npts)))
+    ctx = DeviceContext.get(dev)
+    Yo = B + 0.41 * po.KronSumOperator([tuple(S2.Ms)]).dot(X)
+    fused = S2.apply(x, y, EPI_AXPY, b=b, omega=0.41, dot_ptr=ctx.sptr(21), dot_with=z)
+    got = y.toarray().reshape(Yo.shape)
+    assert np.abs(got - Yo).max() < 1e-13 * np.abs(Yo).max()
+    assert fused, "the TMA kernel should have taken the fused reduction"
+    want = float(np.vdot(Yo, Z))
+    assert abs(ctx.scal[21].item() - want) < 1e-11 * np.abs(Yo * Z).sum()
+    # in place (b is y), as the smoother calls it
+    y2 = StencilVector.from_array(V, B)
+    fused = S2.apply(x, y2, EPI_AXPY, b=y2, omega=0.41, dot_ptr=ctx.sptr(21), dot_with=z)
+    assert fused and abs(ctx.scal[21].item() - want) < 1e-11 * np.abs(Yo * Z).sum()
+    assert np.abs(y2.toarray().reshape(Yo.shape) - Yo).max() < 1e-13 * np.abs(Yo).max()
