@@ -1623,30 +1623,50 @@ __global__ void __launch_bounds__(256) axis_gather_strided2_kernel(
     const double2* __restrict__ in, double2* __restrict__ out, const int32_t* __restrict__ start,
     const double* __restrict__ coef, int W, int n_in, int n_out, int64_t so_in2, int64_t sa_in2,
     int64_t so_out2, int64_t sa_out2, int64_t n_inner2) {
+    // One output row (plane) per blockIdx.y: its <= 8 taps are block-uniform.  Taps with a ZERO
+    // coefficient are skipped (knot-insertion rows carry p+1 slots of which 2-3 are used: a quarter to
+    // a half of the input planes used to be read for nothing), and every thread works on two column
+    // pairs at once (two independent load streams per tap).
     const int i = blockIdx.y;
     const int64_t o = blockIdx.z;
     const int s0 = __ldg(start + i);
     const double* cf = coef + (int64_t)i * W;
     const double2* ip = in + o * so_in2;
     double2* op = out + o * so_out2 + (int64_t)i * sa_out2;
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_inner2;
-         c += (int64_t)gridDim.x * blockDim.x) {
-        double2 v = make_double2(0.0, 0.0);
-        for (int w = 0; w < W; ++w) {
-            const int j = s0 + w;
-            if (j >= 0 && j < n_in) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_inner2; c += 2 * stride) {
+        const int64_t c1 = c + stride;
+        const bool ok1 = c1 < n_inner2;
+        double2 old0 = make_double2(0.0, 0.0), old1 = make_double2(0.0, 0.0);
+        if (ACC) {
+            old0 = op[c];
+            if (ok1) old1 = op[c1];
+        }
+        double2 v0 = make_double2(0.0, 0.0), v1 = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            if (w < W) {
+                const int j = s0 + w;
                 const double cw = __ldg(cf + w);
-                const double2 x = ip[(int64_t)j * sa_in2 + c];
-                v.x = fma(cw, x.x, v.x);
-                v.y = fma(cw, x.y, v.y);
+                if (cw != 0.0 && j >= 0 && j < n_in) {
+                    const double2* row = ip + (int64_t)j * sa_in2;
+                    const double2 x0 = row[c];
+                    const double2 x1 = ok1 ? row[c1] : make_double2(0.0, 0.0);
+                    v0.x = fma(cw, x0.x, v0.x);
+                    v0.y = fma(cw, x0.y, v0.y);
+                    v1.x = fma(cw, x1.x, v1.x);
+                    v1.y = fma(cw, x1.y, v1.y);
+                }
             }
         }
         if (ACC) {
-            const double2 old = op[c];
-            v.x += old.x;
-            v.y += old.y;
+            v0.x += old0.x;
+            v0.y += old0.y;
+            v1.x += old1.x;
+            v1.y += old1.y;
         }
-        op[c] = v;
+        op[c] = v0;
+        if (ok1) op[c1] = v1;
     }
 }
 
@@ -1658,7 +1678,7 @@ extern "C" int poms_axis_gather(const double* in, double* out, const int32_t* st
     if (W < 1 || n_in < 1 || n_out < 1 || n_outer < 1 || n_inner < 1) return bad_arg(5, "extent");
     const bool even = !((n_inner | so_in | sa_in | so_out | sa_out) & 1) &&
                       !(((uintptr_t)in | (uintptr_t)out) & 15);
-    if (even && n_inner >= 64 && n_out <= 65535 && n_outer <= 65535) {
+    if (even && n_inner >= 64 && n_out <= 65535 && n_outer <= 65535 && W <= 8) {
         const int64_t n2 = n_inner / 2;
         int gx = (int)((n2 + 511) / 512);   // ~2 double2 per thread
         if (gx < 1) gx = 1;
