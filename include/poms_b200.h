@@ -244,6 +244,26 @@ int poms_prolong_3d(const double* coarse, double* fine, int n1f, int n2f, int n3
                     const double* c2, int W2, const int32_t* s3, const double* c3, int W3,
                     const int32_t* s2_host, const int32_t* s3_host, int accumulate, void* stream);
 
+/*
+ * Round-2 one-pass transfers for the big levels (poms_transfer3d_v2.cu): same arguments, rows and
+ * results as poms_restrict_3d / poms_prolong_3d, but ONE row width on all three axes (restriction
+ * 3..7, prolongation 2..6).  The in-plane passes run once per COARSE plane and the axis-1 pass lives
+ * in registers, so that 9 (restriction) / 17 (prolongation + correction, mg_jac.py:112) bytes per
+ * fine point move through HBM instead of the 21 / 29 of three per-axis gathers.  A negative status
+ * means "rows do not fit": fall back to poms_restrict_3d / poms_prolong_3d / poms_axis_gather.
+ */
+int poms_restrict_3d_v2(const double* fine, double* coarse, int n1f, int n2f, int n3f, int64_t ldf,
+                        int64_t pldf, int n1c, int n2c, int n3c, int64_t ldc, int64_t pldc,
+                        const int32_t* s1, const double* c1, int W1, const int32_t* s2,
+                        const double* c2, int W2, const int32_t* s3, const double* c3, int W3,
+                        const int32_t* s1_host, const int32_t* s2_host, const int32_t* s3_host,
+                        void* stream);
+int poms_prolong_3d_v2(const double* coarse, double* fine, int n1f, int n2f, int n3f, int64_t ldf,
+                       int64_t pldf, int n1c, int n2c, int n3c, int64_t ldc, int64_t pldc,
+                       const int32_t* s1, const double* c1, int W1, const int32_t* s2,
+                       const double* c2, int W2, const int32_t* s3, const double* c3, int W3,
+                       const int32_t* s2_host, const int32_t* s3_host, int accumulate, void* stream);
+
 /* y = Ainv x, dense row-major n x n (replicated coarse direct solve, sources/mg_jac.py:98-99) */
 int poms_dense_matvec(const double* Ainv, const double* x, double* y, int n, void* stream);
 

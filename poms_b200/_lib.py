@@ -54,6 +54,10 @@ _PROTOS = {
                                   _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "poms_prolong_3d": (C.c_int, [_vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _l, _l,
                                  _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "poms_restrict_3d_v2": (C.c_int, [_vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _l, _l,
+                                     _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "poms_prolong_3d_v2": (C.c_int, [_vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _l, _l,
+                                    _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "poms_stencil_matvec_3d": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _i, _i,
                                         _i, _d, _vp, _vp, _vp]),
     "poms_color_add": (C.c_int, [_vp, _vp, _i, _i, _i, _l, _l, _i, _i, _vp]),

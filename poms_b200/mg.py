@@ -102,10 +102,20 @@ def _pitch(n):
     return n + (n & 1)
 
 
-def _fused_restrict(ops, fine, shape_f, ld_f, coarse, shape_c, ld_c):
+def transfer_v2_min():
+    """Fine points per rank from which the one-pass transfers use the round-2 big-level kernels
+    (poms_transfer3d_v2.cu); below, the round-1 one-pass kernels (latency-bound levels).
+    POMS_B200_TRANSFER_V2=0 switches the big-level kernels off (per-axis gathers there, as before)."""
+    if os.environ.get("POMS_B200_TRANSFER_V2", "1") == "0":
+        return None
+    return int(os.environ.get("POMS_B200_TRANSFER_V2_MIN", "6000000"))
+
+
+def _fused_restrict(ops, fine, shape_f, ld_f, coarse, shape_c, ld_c, v2=False):
     """coarse = (R1 (x) R2 (x) R3) fine in one kernel; False if the rows do not fit its tiles."""
     r1, r2, r3 = ops
-    rc = _lib.lib().poms_restrict_3d(
+    fn = _lib.lib().poms_restrict_3d_v2 if v2 else _lib.lib().poms_restrict_3d
+    rc = fn(
         fine.data_ptr(), coarse.data_ptr(), shape_f[0], shape_f[1], shape_f[2], ld_f,
         shape_f[1] * ld_f, shape_c[0], shape_c[1], shape_c[2], ld_c, shape_c[1] * ld_c,
         r1.start.data_ptr(), r1.coef.data_ptr(), r1.W, r2.start.data_ptr(), r2.coef.data_ptr(), r2.W,
@@ -117,10 +127,11 @@ def _fused_restrict(ops, fine, shape_f, ld_f, coarse, shape_c, ld_c):
     return True
 
 
-def _fused_prolong(ops, coarse, shape_c, ld_c, fine, shape_f, ld_f, accumulate):
+def _fused_prolong(ops, coarse, shape_c, ld_c, fine, shape_f, ld_f, accumulate, v2=False):
     """fine (+)= (P1 (x) P2 (x) P3) coarse in one kernel; False if the rows do not fit its tiles."""
     p1, p2, p3 = ops
-    rc = _lib.lib().poms_prolong_3d(
+    fn = _lib.lib().poms_prolong_3d_v2 if v2 else _lib.lib().poms_prolong_3d
+    rc = fn(
         coarse.data_ptr(), fine.data_ptr(), shape_f[0], shape_f[1], shape_f[2], ld_f,
         shape_f[1] * ld_f, shape_c[0], shape_c[1], shape_c[2], ld_c, shape_c[1] * ld_c,
         p1.start.data_ptr(), p1.coef.data_ptr(), p1.W, p2.start.data_ptr(), p2.coef.data_ptr(), p2.W,
@@ -167,11 +178,26 @@ class Transfer:
         # 0.045 / 0.044 ms vs 0.085 / 0.073 ms at 131^3, but 0.77 / 1.41 ms vs 0.61 / 1.01 ms at 515^3,
         # where the three streaming passes run closer to the HBM rate than the fused tile pipeline)
         self.fused = self.ndim == 3 and all(op is not None for op in self.P)
-        self.fused_max = 6_000_000      # fine points per rank up to which the fused kernels are used
+        self.fused_max = 6_000_000      # fine points per rank up to which the round-1 fused kernels are used
+        # bigger levels: the round-2 one-pass kernels (poms_transfer3d_v2.cu; tests/gpu_ab_transfer.py)
+        self.v2_min = transfer_v2_min()
+        self.fused_v2 = self.fused and self.v2_min is not None
         self._tmps = {}
 
     def _want_fused(self, shape_f):
-        return self.fused and int(np.prod(shape_f)) <= self.fused_max
+        """None (per-axis gathers), "v1" (round-1 one-pass kernels) or "v2" (big-level kernels)."""
+        n = int(np.prod(shape_f))
+        if self.fused and n <= self.fused_max:
+            return "v1"
+        if self.fused_v2 and n >= self.v2_min:
+            return "v2"
+        return None
+
+    def _fused_failed(self, kind):
+        if kind == "v2":
+            self.fused_v2 = False
+        else:
+            self.fused = False
 
     def _tmp(self, key, shape, ld):
         """Intermediate array of a per-axis pass, allocated (and zeroed: pad column) once per
@@ -190,10 +216,12 @@ class Transfer:
         rc = StencilVector(Vc) if out is None else out
         cur, ld = rf.flat, rf.ld
         shape = tuple(rf.space.local_shape)
-        if self._want_fused(shape):
-            if _fused_restrict(self.R, cur, shape, ld, rc.flat, tuple(Vc.local_shape), rc.ld):
+        kind = self._want_fused(shape)
+        if kind:
+            if _fused_restrict(self.R, cur, shape, ld, rc.flat, tuple(Vc.local_shape), rc.ld,
+                               v2=(kind == "v2")):
                 return rc
-            self.fused = False
+            self._fused_failed(kind)
         ops = [(ax, op) for ax, op in enumerate(self.R) if op is not None]
         if not ops:
             rc.flat.copy_(cur)
@@ -216,11 +244,12 @@ class Transfer:
         pass along axis 1 accumulates straight into x_f (correction fused, mg_jac.py:112)."""
         cur, ld = ec.flat, ec.ld
         shape = tuple(ec.space.local_shape)
-        if self._want_fused(xf.space.local_shape):
+        kind = self._want_fused(xf.space.local_shape)
+        if kind:
             if _fused_prolong(self.P, cur, shape, ld, xf.flat, tuple(xf.space.local_shape), xf.ld,
-                              True):
+                              True, v2=(kind == "v2")):
                 return xf
-            self.fused = False
+            self._fused_failed(kind)
         ops = [(ax, op) for ax, op in reversed(list(enumerate(self.P))) if op is not None]
         if not ops:
             xf.flat.add_(cur)
@@ -285,16 +314,17 @@ class DistTransfer(Transfer):
         if planes is None:
             planes = slab.gather_planes(rf.flat, self.tf, self.need_f)
         shape_f = (planes.shape[0],) + tuple(rf.space.local_shape[1:])
-        if self._want_fused(shape_f):
+        kind = self._want_fused(shape_f)
+        if kind:
             rc = StencilVector(Vc) if out is None else out
             shape_c = (ce - cs + 1,) + tuple(Vc.local_shape[1:])
             dst = rc.flat if self.cdist else _tmp(shape_c, rc.ld, self.device)
             if _fused_restrict((self.R0, self.R[1], self.R[2]), planes, shape_f, ld, dst, shape_c,
-                               rc.ld):
+                               rc.ld, v2=(kind == "v2")):
                 if not self.cdist:
                     rc.flat.copy_(slab.allgather_planes(dst, self.tc))
                 return rc
-            self.fused = False
+            self._fused_failed(kind)
         shape = (planes.shape[0],) + tuple(rf.space.local_shape[1:])
         ops = [(ax, op) for ax, op in enumerate(self.R) if op is not None and ax > 0]
         rc = StencilVector(Vc) if out is None else out
@@ -334,11 +364,12 @@ class DistTransfer(Transfer):
         if gview is not None:
             cur = gview
             shape = (cur.shape[0],) + tuple(shape[1:])
-        if (gview is not None or not self.cdist) and self._want_fused(xf.space.local_shape):
+        kind = self._want_fused(xf.space.local_shape) if (gview is not None or not self.cdist) else None
+        if kind:
             if _fused_prolong((self.P0, self.P[1], self.P[2]), cur, shape, ld, xf.flat,
-                              tuple(xf.space.local_shape), xf.ld, True):
+                              tuple(xf.space.local_shape), xf.ld, True, v2=(kind == "v2")):
                 return xf
-            self.fused = False
+            self._fused_failed(kind)
         ops = [(ax, op) for ax, op in reversed(list(enumerate(self.P))) if op is not None and ax > 0]
         for ax, op in ops:
             shape_out = list(shape)

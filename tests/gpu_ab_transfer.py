@@ -21,8 +21,9 @@ while N >= 64:
     rf.data.copy_(torch.randn(Vf.npts, generator=g, dtype=torch.float64, device=dev))
     ec.data.copy_(torch.randn(Vc.npts, generator=g, dtype=torch.float64, device=dev))
     res = {}
-    for fused in (False, True):
-        tr.fused, tr.fused_max = fused, 10 ** 12
+    for fused in (False, True, "v2"):
+        tr.fused, tr.fused_max = fused is True, (10 ** 12 if fused is True else -1)
+        tr.fused_v2, tr.v2_min = fused == "v2", 0
         xf.flat.zero_()
         rc = tr.restrict(rf, Vc)
         tr.prolong_add(ec, xf)
@@ -38,9 +39,15 @@ while N >= 64:
                 fn()
             e1.record()
             torch.cuda.synchronize()
-            print("n=%4d %-12s %-8s %8.4f ms" % (N + p, name, "fused" if fused else "per-axis", e0.elapsed_time(e1) / reps), flush=True)
-        assert tr.fused == fused
-    dr = (res[True][0] - res[False][0]).abs().max().item() / res[False][0].abs().max().item()
-    dp = (res[True][1] - res[False][1]).abs().max().item() / res[False][1].abs().max().item()
-    print("   max rel diff fused vs per-axis: restrict %.1e prolong %.1e" % (dr, dp))
+            ms = e0.elapsed_time(e1) / reps
+            nbytes = 8 * ((N + p) ** 3 * (1 if name == "restrict" else 2) + (N // 2 + p) ** 3)
+            print("n=%4d %-12s %-8s %8.4f ms  %6.0f GB/s (algorithmic)" % (
+                N + p, name, {False: "per-axis", True: "fused", "v2": "fused-v2"}[fused], ms,
+                nbytes / ms * 1e-6), flush=True)
+        assert tr._want_fused(Vf.npts) == {False: None, True: "v1", "v2": "v2"}[fused]
+    for k in (True, "v2"):
+        dr = (res[k][0] - res[False][0]).abs().max().item() / res[False][0].abs().max().item()
+        dp = (res[k][1] - res[False][1]).abs().max().item() / res[False][1].abs().max().item()
+        print("   max rel diff %s vs per-axis: restrict %.1e prolong %.1e" % (
+            "fused" if k is True else "fused-v2", dr, dp))
     N //= 2

@@ -407,15 +407,21 @@ def test_transfer_and_coarse_solver_vs_oracle(dev, p, N):
         P1s.append(po.insertion_matrix(ts, Nc[a] + p, p, Tc[a]))
     rng = np.random.default_rng(11)
     rf, ec, xf = rng.standard_normal(Vf.npts), rng.standard_normal(Vc.npts), rng.standard_normal(Vf.npts)
-    # 3-D: the fused one-pass kernels (poms_restrict_3d / poms_prolong_3d), then the per-axis gathers
-    for fused in ([True, False] if d == 3 else [False]):
+    # 3-D: the one-pass kernels of the small levels (poms_restrict_3d / poms_prolong_3d), the one-pass
+    # kernels of the big levels (poms_*_3d_v2), then the per-axis gathers
+    same_w = len({op.W for op in tr.R}) == 1 and len({op.W for op in tr.P}) == 1
+    for kind in (["v1", "v2", None] if d == 3 else [None]):
         assert tr.fused == (d == 3)
-        tr.fused, tr.fused_max = fused, 10 ** 12
+        if kind == "v2" and not same_w:
+            continue                        # v2 needs one row width on all axes (mixed tiny grids)
+        tr.fused, tr.fused_max = kind == "v1", (10 ** 12 if kind == "v1" else -1)
+        tr.fused_v2, tr.v2_min = kind == "v2", 0
+        assert tr._want_fused(Vf.npts) == kind
         assert rel(_arr(tr.restrict(_vec(Vf, rf), Vc)), po.restrict(P1s, rf)) < 1e-13
         x = _vec(Vf, xf)
         tr.prolong_add(_vec(Vc, ec), x)
         assert rel(_arr(x), xf + po.prolong(P1s, ec)) < 1e-13
-        assert tr.fused == fused            # no silent fall-back to the gathers
+        assert tr._want_fused(Vf.npts) == kind   # no silent fall-back to the gathers
         tr.fused = d == 3
     if max(N) > 64:
         return
@@ -424,6 +430,56 @@ def test_transfer_and_coarse_solver_vs_oracle(dev, p, N):
     bc = rng.standard_normal(Vc.npts)
     xo = np.linalg.solve(Aco.tocsr().toarray(), bc.ravel()).reshape(bc.shape)
     assert rel(_arr(CoarseSolver(Ac, dev).solve(_vec(Vc, bc))), xo) < 1e-10
+
+
+@pytest.mark.parametrize("p,N,size", [(3, (48, 20, 70), 2), (2, (40, 36, 24), 3), (3, (132, 24, 136), 4)])
+def test_transfer_v2_slab_rows(dev, p, N, size):
+    """The big-level one-pass kernels on the row tables of a slab plan (dist.slab_transfer_plan:
+    starts relative to a rank's plane block, rows cut at the block ends), every rank's block
+    emulated on one device, against the oracle restricted to that rank's planes."""
+    from poms_b200 import bsplines as bs
+    from poms_b200.dist import slab_transfer_plan
+    from poms_b200.mg import Transfer, _AxisOp, _fused_restrict, _fused_prolong, _pitch
+    from oracle import poms_oracle as po
+    Nc = [n // 2 for n in N]
+    Tf = [bs.make_open_knots(p, n + p) for n in N]
+    Tc = [bs.make_open_knots(p, n + p) for n in Nc]
+    nf, nc = [n + p for n in N], [n + p for n in Nc]
+    tr = Transfer(Tc, Tf, p, dev)
+    P1s = []
+    for a in range(3):
+        ts = po.knots_to_insert(Tf[a], nf[a], p, Tc[a], nc[a], p)
+        P1s.append(po.insertion_matrix(ts, nc[a], p, Tc[a]))
+    rng = np.random.default_rng(5)
+    rf, ec, xf = rng.standard_normal(nf), rng.standard_normal(nc), rng.standard_normal(nf)
+    rc_ref, xf_ref = po.restrict(P1s, rf), xf + po.prolong(P1s, ec)
+    st, cf, n_c = tr.P1_rows[0]
+    plan = slab_transfer_plan(st, cf, n_c, size, True)
+    ldf, ldc = _pitch(nf[2]), _pitch(nc[2])
+
+    def pitched(a, ld):
+        t = torch.zeros(a.shape[:2] + (ld,), dtype=torch.float64, device=dev)
+        t[:, :, :a.shape[2]] = torch.as_tensor(a, device=dev)
+        return t
+
+    for q in range(size):
+        (fs, fe), (cs, ce) = plan["tf"][q], plan["tc"][q]
+        lo, hi = plan["need_f"][q]
+        R0 = _AxisOp(*plan["R0"][q], dev)
+        planes = pitched(rf[lo:hi + 1], ldf)
+        out = torch.zeros((ce - cs + 1, nc[1], ldc), dtype=torch.float64, device=dev)
+        assert _fused_restrict((R0, tr.R[1], tr.R[2]), planes, (hi - lo + 1, nf[1], nf[2]), ldf, out,
+                               (ce - cs + 1, nc[1], nc[2]), ldc, v2=True)
+        assert rel(out[:, :, :nc[2]].cpu().numpy(), rc_ref[cs:ce + 1]) < 1e-13
+        assert not out[:, :, nc[2]:].any()
+        lo, hi = plan["need_c"][q]
+        P0 = _AxisOp(*plan["P0"][q], dev)
+        cpl = pitched(ec[lo:hi + 1], ldc)
+        x = pitched(xf[fs:fe + 1], ldf)
+        assert _fused_prolong((P0, tr.P[1], tr.P[2]), cpl, (hi - lo + 1, nc[1], nc[2]), ldc, x,
+                              (fe - fs + 1, nf[1], nf[2]), ldf, True, v2=True)
+        assert rel(x[:, :, :nf[2]].cpu().numpy(), xf_ref[fs:fe + 1]) < 1e-13
+        assert not x[:, :, nf[2]:].any()
 
 
 # ----------------------------------------------------------------------------- f1 MG-PCG (extension)
