@@ -19,6 +19,8 @@ EXTENSION beyond the reference (labelled in every report
 """
 from math import sqrt
 
+import os
+
 import numpy as np
 import torch
 
@@ -103,12 +105,16 @@ def _pitch(n):
 
 
 def transfer_v2_min():
-    """Fine points per rank from which the one-pass transfers use the round-2 big-level kernels
-    (poms_transfer3d_v2.cu); below, the round-1 one-pass kernels (latency-bound levels).
-    POMS_B200_TRANSFER_V2=0 switches the big-level kernels off (per-axis gathers there, as before)."""
-    if os.environ.get("POMS_B200_TRANSFER_V2", "1") == "0":
-        return None
-    return int(os.environ.get("POMS_B200_TRANSFER_V2_MIN", "6000000"))
+    """Fine points per rank from which a transfer uses the round-2 one-pass kernels
+    (poms_transfer3d_v2.cu), per operation; None = never.  Measured at p = 3
+    (profiles/r02_ab_transfer_v2.txt): the prolongation wins at every size from 131^3 up (515^3: 0.71 ms
+    against 0.96 ms for three per-axis gathers and 1.41 ms for the round-1 one-pass kernel), the
+    restriction only ties (0.66 vs 0.63 ms), so it stays on the gathers unless
+    POMS_B200_TRANSFER_V2=all.  POMS_B200_TRANSFER_V2=0 switches both off."""
+    mode = os.environ.get("POMS_B200_TRANSFER_V2", "prolong")
+    if mode == "0":
+        return {"restrict": None, "prolong": None}
+    return {"restrict": 6_000_000 if mode == "all" else None, "prolong": 1_000_000}
 
 
 def _fused_restrict(ops, fine, shape_f, ld_f, coarse, shape_c, ld_c, v2=False):
@@ -179,18 +185,21 @@ class Transfer:
         # where the three streaming passes run closer to the HBM rate than the fused tile pipeline)
         self.fused = self.ndim == 3 and all(op is not None for op in self.P)
         self.fused_max = 6_000_000      # fine points per rank up to which the round-1 fused kernels are used
-        # bigger levels: the round-2 one-pass kernels (poms_transfer3d_v2.cu; tests/gpu_ab_transfer.py)
+        # round-2 one-pass kernels (poms_transfer3d_v2.cu; tests/gpu_ab_transfer.py): thresholds per
+        # operation (a dict, or one number for both)
         self.v2_min = transfer_v2_min()
-        self.fused_v2 = self.fused and self.v2_min is not None
+        self.fused_v2 = self.fused
         self._tmps = {}
 
-    def _want_fused(self, shape_f):
-        """None (per-axis gathers), "v1" (round-1 one-pass kernels) or "v2" (big-level kernels)."""
+    def _want_fused(self, shape_f, op):
+        """None (per-axis gathers), "v1" (round-1 one-pass kernels) or "v2" (round-2 kernels) for
+        `op` = "restrict" / "prolong" on a fine grid of this shape."""
         n = int(np.prod(shape_f))
+        v2_min = self.v2_min.get(op) if isinstance(self.v2_min, dict) else self.v2_min
+        if self.fused_v2 and v2_min is not None and n >= v2_min:
+            return "v2"
         if self.fused and n <= self.fused_max:
             return "v1"
-        if self.fused_v2 and n >= self.v2_min:
-            return "v2"
         return None
 
     def _fused_failed(self, kind):
@@ -216,7 +225,7 @@ class Transfer:
         rc = StencilVector(Vc) if out is None else out
         cur, ld = rf.flat, rf.ld
         shape = tuple(rf.space.local_shape)
-        kind = self._want_fused(shape)
+        kind = self._want_fused(shape, "restrict")
         if kind:
             if _fused_restrict(self.R, cur, shape, ld, rc.flat, tuple(Vc.local_shape), rc.ld,
                                v2=(kind == "v2")):
@@ -244,7 +253,7 @@ class Transfer:
         pass along axis 1 accumulates straight into x_f (correction fused, mg_jac.py:112)."""
         cur, ld = ec.flat, ec.ld
         shape = tuple(ec.space.local_shape)
-        kind = self._want_fused(xf.space.local_shape)
+        kind = self._want_fused(xf.space.local_shape, "prolong")
         if kind:
             if _fused_prolong(self.P, cur, shape, ld, xf.flat, tuple(xf.space.local_shape), xf.ld,
                               True, v2=(kind == "v2")):
@@ -314,7 +323,7 @@ class DistTransfer(Transfer):
         if planes is None:
             planes = slab.gather_planes(rf.flat, self.tf, self.need_f)
         shape_f = (planes.shape[0],) + tuple(rf.space.local_shape[1:])
-        kind = self._want_fused(shape_f)
+        kind = self._want_fused(shape_f, "restrict")
         if kind:
             rc = StencilVector(Vc) if out is None else out
             shape_c = (ce - cs + 1,) + tuple(Vc.local_shape[1:])
@@ -364,7 +373,8 @@ class DistTransfer(Transfer):
         if gview is not None:
             cur = gview
             shape = (cur.shape[0],) + tuple(shape[1:])
-        kind = self._want_fused(xf.space.local_shape) if (gview is not None or not self.cdist) else None
+        kind = (self._want_fused(xf.space.local_shape, "prolong")
+                if (gview is not None or not self.cdist) else None)
         if kind:
             if _fused_prolong((self.P0, self.P[1], self.P[2]), cur, shape, ld, xf.flat,
                               tuple(xf.space.local_shape), xf.ld, True, v2=(kind == "v2")):

@@ -1,5 +1,5 @@
 """A/B timing of the grid transfers: fused one-pass kernels vs per-axis gathers -- run on the GPU box:
-    python tests/gpu_ab_transfer.py [N] [p]"""
+    python tests/gpu_ab_transfer.py [N] [p] [Nmin]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -9,9 +9,10 @@ from poms_b200.stencil import StencilVectorSpace, StencilVector
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 p = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+Nmin = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(0)
-while N >= 64:
+while N >= Nmin:
     Tf = [bs.make_open_knots(p, N + p)] * 3
     Tc = [bs.make_open_knots(p, N // 2 + p)] * 3
     Vf = StencilVectorSpace([N + p] * 3, [p] * 3, [False] * 3, device=dev)
@@ -44,7 +45,8 @@ while N >= 64:
             print("n=%4d %-12s %-8s %8.4f ms  %6.0f GB/s (algorithmic)" % (
                 N + p, name, {False: "per-axis", True: "fused", "v2": "fused-v2"}[fused], ms,
                 nbytes / ms * 1e-6), flush=True)
-        assert tr._want_fused(Vf.npts) == {False: None, True: "v1", "v2": "v2"}[fused]
+        for op in ("restrict", "prolong"):
+            assert tr._want_fused(Vf.npts, op) == {False: None, True: "v1", "v2": "v2"}[fused]
     for k in (True, "v2"):
         dr = (res[k][0] - res[False][0]).abs().max().item() / res[False][0].abs().max().item()
         dp = (res[k][1] - res[False][1]).abs().max().item() / res[False][1].abs().max().item()

@@ -416,12 +416,13 @@ def test_transfer_and_coarse_solver_vs_oracle(dev, p, N):
             continue                        # v2 needs one row width on all axes (mixed tiny grids)
         tr.fused, tr.fused_max = kind == "v1", (10 ** 12 if kind == "v1" else -1)
         tr.fused_v2, tr.v2_min = kind == "v2", 0
-        assert tr._want_fused(Vf.npts) == kind
+        assert tr._want_fused(Vf.npts, "restrict") == tr._want_fused(Vf.npts, "prolong") == kind
         assert rel(_arr(tr.restrict(_vec(Vf, rf), Vc)), po.restrict(P1s, rf)) < 1e-13
         x = _vec(Vf, xf)
         tr.prolong_add(_vec(Vc, ec), x)
         assert rel(_arr(x), xf + po.prolong(P1s, ec)) < 1e-13
-        assert tr._want_fused(Vf.npts) == kind   # no silent fall-back to the gathers
+        # no silent fall-back to the gathers
+        assert tr._want_fused(Vf.npts, "restrict") == tr._want_fused(Vf.npts, "prolong") == kind
         tr.fused = d == 3
     if max(N) > 64:
         return
