@@ -252,8 +252,6 @@ int poms_prolong_3d(const double* coarse, double* fine, int n1f, int n2f, int n3
  * fine point move through HBM instead of the 21 / 29 of three per-axis gathers.  A negative status
  * means "rows do not fit": fall back to poms_restrict_3d / poms_prolong_3d / poms_axis_gather.
  */
-void poms_set_transfer_variant(int v);   /* A/B timing only: bit 0 = table-driven restriction, bit 1 =
-                                            prolongation with two CTAs per SM (default 3) */
 int poms_restrict_3d_v2(const double* fine, double* coarse, int n1f, int n2f, int n3f, int64_t ldf,
                         int64_t pldf, int n1c, int n2c, int n3c, int64_t ldc, int64_t pldc,
                         const int32_t* s1, const double* c1, int W1, const int32_t* s2,

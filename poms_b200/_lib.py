@@ -54,7 +54,6 @@ _PROTOS = {
                                   _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "poms_prolong_3d": (C.c_int, [_vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _l, _l,
                                  _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
-    "poms_set_transfer_variant": (None, [_i]),
     "poms_restrict_3d_v2": (C.c_int, [_vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _l, _l,
                                      _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "poms_prolong_3d_v2": (C.c_int, [_vp, _vp, _i, _i, _i, _l, _l, _i, _i, _i, _l, _l,

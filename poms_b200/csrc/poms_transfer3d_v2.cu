@@ -76,8 +76,8 @@ constexpr int P2_GS = P2_RC3 + 1;
 // coarse-tile points per thread: the true extent nr2 x nr3 is <= 256 * p2_ng(W) (host-checked)
 __host__ __device__ constexpr int p2_ng(int W) { return W >= 6 ? 3 : 2; }
 
-template <int W, int MINB>
-__global__ void __launch_bounds__(256, MINB) prolong3d_v2_kernel(const TR3 a) {
+template <int W>
+__global__ void __launch_bounds__(256, 3) prolong3d_v2_kernel(const TR3 a) {
     __shared__ double G[(P2_RC2 + 1) * P2_GS];
     __shared__ double H[(P2_RC2 + 8) * P2_F3];
     __shared__ double c2s[P2_F2 * W];
@@ -144,9 +144,9 @@ __global__ void __launch_bounds__(256, MINB) prolong3d_v2_kernel(const TR3 a) {
 
     double* xp = a.dst + (int64_t)j_lo * a.pldf + (int64_t)(f2_0 + ty) * a.ldf + f3_0 + tx;
     const int64_t rstep = 4 * a.ldf;
-    // x of the planes j, j+1 (and j+2 when the register budget of two CTAs per SM allows it)
-    constexpr bool DEEP = MINB <= 2;
-    double xa[4], xb[4], xc[DEEP ? 4 : 1];
+    // x of the planes j and j+1 (a third plane in flight at two CTAs per SM, without the 20 bytes of
+    // spills of this version, measured slower: 0.80 vs 0.72 ms at 515^3)
+    double xa[4], xb[4];
     auto load_x = [&](double (&x)[4], const double* p, const bool live) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -155,7 +155,6 @@ __global__ void __launch_bounds__(256, MINB) prolong3d_v2_kernel(const TR3 a) {
     const bool acc_in = a.accumulate != 0;
     load_x(xa, xp, acc_in);
     load_x(xb, xp + a.pldf, acc_in && j_lo + 1 < j_hi);
-    if constexpr (DEEP) load_x(xc, xp + 2 * a.pldf, acc_in && j_lo + 2 < j_hi);
 
     double g[W][4];
 #pragma unroll
@@ -214,18 +213,9 @@ __global__ void __launch_bounds__(256, MINB) prolong3d_v2_kernel(const TR3 a) {
             for (int k = 0; k < W; ++k) v = fma(w1[k], g[k][q], v);
             if (okmask >> q & 1u) xp[q * rstep] = v;
         }
-        if constexpr (DEEP) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                xa[q] = xb[q];
-                xb[q] = xc[q];
-            }
-            load_x(xc, xp + 3 * a.pldf, acc_in && j + 3 < j_hi);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) xa[q] = xb[q];
-            load_x(xb, xp + 2 * a.pldf, acc_in && j + 2 < j_hi);
-        }
+        for (int q = 0; q < 4; ++q) xa[q] = xb[q];
+        load_x(xb, xp + 2 * a.pldf, acc_in && j + 2 < j_hi);
         xp += a.pldf;
     }
 }
@@ -233,142 +223,20 @@ __global__ void __launch_bounds__(256, MINB) prolong3d_v2_kernel(const TR3 a) {
 // ---------------------------------------------------------------------------------------------
 // Restriction.  CTA: 8 x 32 coarse tile of axes (2, 3) (one point per thread), marching along the
 // FINE planes of a chunk of coarse planes.  Every thread owns NPT points of the halo'd fine tile:
-//   per fine plane j:            acc[s] += R1[i_cur+s][j - start] * fine[j]   (registers, scatter form)
+//   per fine plane j:            acc[s] += R1[base(j)+s][j - start] * fine[j]  (registers, scatter form)
 //   per completed coarse plane:  F = acc[0] (registers -> shared), H = F restricted along axis 3,
 //                                out = H restricted along axis 2 -> global
-// ---------------------------------------------------------------------------------------------
-constexpr int R2_C2 = 8, R2_C3 = 32, R2_RF2 = 22, R2_RF3 = 72, R2_MAXCH = 64;
-constexpr int R2_FS = R2_RF3 + 1;
-
-template <int W, int NPT, int NS>
-__global__ void __launch_bounds__(256, 2) restrict3d_v2_kernel(const TR3 a) {
-    __shared__ double F[(R2_RF2 + 1) * R2_FS];
-    __shared__ double H[(R2_RF2 + 8) * R2_C3];
-    __shared__ double c2s[R2_C2 * W];
-    __shared__ double c1s[R2_MAXCH * W];
-    __shared__ int s1s[R2_MAXCH];
-    const int tid = threadIdx.x;
-    const int tx = tid & (R2_C3 - 1), ty = tid >> 5;
-    const int c3_0 = blockIdx.x * R2_C3, c2_0 = blockIdx.y * R2_C2;
-    const int i_lo = blockIdx.z * a.chunk, i_hi = min(a.n1c, i_lo + a.chunk);
-    const int c3l = min(R2_C3, a.n3c - c3_0), c2l = min(R2_C2, a.n2c - c2_0);
-    const int f2lo = a.s2[c2_0], f3lo = a.s3[c3_0];
-    const int f2hi = min(a.n2f - 1, a.s2[c2_0 + c2l - 1] + W - 1);
-    const int f3hi = min(a.n3f - 1, a.s3[c3_0 + c3l - 1] + W - 1);
-    const int nf2 = f2hi - f2lo + 1, nf3 = f3hi - f3lo + 1;
-    const bool v3 = tx < c3l, v2 = ty < c2l;
-
-    for (int t = tid; t < (R2_RF2 + 1) * R2_FS; t += 256) F[t] = 0.0;
-    for (int t = tid; t < (R2_RF2 + 8) * R2_C3; t += 256) H[t] = 0.0;
-    for (int t = tid; t < R2_C2 * W; t += 256) {
-        const int r = t / W;
-        c2s[t] = r < c2l ? a.c2[(int64_t)c2_0 * W + t] : 0.0;
-    }
-    for (int t = tid; t < (i_hi - i_lo) * W; t += 256) c1s[t] = a.c1[(int64_t)i_lo * W + t];
-    for (int t = tid; t < i_hi - i_lo; t += 256) s1s[t] = a.s1[i_lo + t];
-
-    double c3r[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) c3r[k] = v3 ? a.c3[(int64_t)(c3_0 + tx) * W + k] : 0.0;
-    const int o3 = v3 ? a.s3[c3_0 + tx] - f3lo : 0;
-    const int o2 = v2 ? a.s2[c2_0 + ty] - f2lo : 0;
-    // this thread's points of the halo'd fine tile (row-major over its true extent nf2 x nf3)
-    int go[NPT], so[NPT];
-    unsigned fmask = 0;
-#pragma unroll
-    for (int m = 0; m < NPT; ++m) {
-        const int slot = tid + 256 * m;
-        const int r = slot / nf3, c = slot - r * nf3;
-        const bool ok = r < nf2;
-        if (ok) fmask |= 1u << m;
-        go[m] = ok ? (int)((int64_t)r * a.ldf) + c : 0;
-        so[m] = ok ? r * R2_FS + c : 0;
-    }
-    __syncthreads();
-
-    // (a slab plan may start a row before its block: those taps carry zero coefficients)
-    const int j_lo = max(0, s1s[0]);
-    const int j_hi = min(a.n1f - 1, s1s[i_hi - 1 - i_lo] + W - 1);
-    const double* fp = a.src + (int64_t)j_lo * a.pldf + (int64_t)f2lo * a.ldf + f3lo;
-    double* const out = a.dst + (int64_t)(c2_0 + ty) * a.ldc + c3_0 + tx;
-    double fa[NPT], fb[NPT];
-    auto load_f = [&](double (&f)[NPT], const double* p, const bool live) {
-#pragma unroll
-        for (int m = 0; m < NPT; ++m) f[m] = (live && (fmask >> m & 1u)) ? __ldcs(p + go[m]) : 0.0;
-    };
-    load_f(fa, fp, true);
-    load_f(fb, fp + a.pldf, j_lo + 1 <= j_hi);
-
-    double acc[NS][NPT];
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-#pragma unroll
-        for (int m = 0; m < NPT; ++m) acc[s][m] = 0.0;
-    int i_cur = i_lo;
-
-#pragma unroll 1
-    for (int j = j_lo; j <= j_hi; ++j) {
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const int i = i_cur + s;
-            if (i < i_hi) {
-                const int t = j - s1s[i - i_lo];
-                if (t >= 0 && t < W) {
-                    const double w = c1s[(i - i_lo) * W + t];
-#pragma unroll
-                    for (int m = 0; m < NPT; ++m) acc[s][m] = fma(w, fa[m], acc[s][m]);
-                }
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < NPT; ++m) fa[m] = fb[m];
-        load_f(fb, fp + 2 * a.pldf, j + 2 <= j_hi);
-        fp += a.pldf;
-#pragma unroll 1
-        while (i_cur < i_hi && (s1s[i_cur - i_lo] + W - 1 <= j || j == j_hi)) {
-#pragma unroll
-            for (int m = 0; m < NPT; ++m)
-                if (fmask >> m & 1u) F[so[m]] = acc[0][m];
-            __syncthreads();
-            if (v3) {
-#pragma unroll 1
-                for (int r = ty; r < nf2; r += 8) {
-                    const double* const fr = F + r * R2_FS + o3;
-                    double hs = c3r[0] * fr[0];
-#pragma unroll
-                    for (int k = 1; k < W; ++k) hs = fma(c3r[k], fr[k], hs);
-                    H[r * R2_C3 + tx] = hs;
-                }
-            }
-            __syncthreads();
-            if (v2 && v3) {
-                const double* const hp = H + o2 * R2_C3 + tx;
-                const double* const cr = c2s + ty * W;
-                double v = cr[0] * hp[0];
-#pragma unroll
-                for (int k = 1; k < W; ++k) v = fma(cr[k], hp[k * R2_C3], v);
-                out[(int64_t)i_cur * a.pldc] = v;
-            }
-#pragma unroll
-            for (int s = 0; s + 1 < NS; ++s)
-#pragma unroll
-                for (int m = 0; m < NPT; ++m) acc[s][m] = acc[s + 1][m];
-#pragma unroll
-            for (int m = 0; m < NPT; ++m) acc[NS - 1][m] = 0.0;
-            ++i_cur;
-        }
-    }
-}
-
-// Restriction, table-driven (variant bit 0).  ncu of the kernel above at 515^3
-// (profiles/r02_ncu_transfer_v2.txt): 2.4 warp instructions per fine point, issue slots 47 % busy at
-// two CTAs per SM -- the per-plane bookkeeping (which coarse rows are open, 4 x [compare, branch,
-// weight look-up], predicated loads, register moves of the prefetch pair) costs more than the
-// arithmetic.  Here each CTA first tabulates, per fine plane j of its chunk, the first open coarse row
+// The first version kept the bookkeeping of the open coarse rows in the march (4 x [compare, branch,
+// weight look-up] per plane, predicated loads, register copies of the prefetch pair): ncu at 515^3
+// (profiles/r02_ncu_transfer_v2_first.txt) showed 2.4 warp instructions per fine point with the issue
+// slots 47 % busy at two CTAs per SM -- instruction bound, 0.665 ms.  This version (0.456 ms) has each
+// CTA first tabulate, per fine plane j of its chunk, the first open coarse row
 // base(j), the weights of j in rows base(j) .. base(j)+NS-1 (zero where j is outside the row) and the
 // number of rows that end at j; the march is then branch-free: NS broadcast weights x NPT FMAs per
 // plane, unpredicated loads (dead slots re-read the tile origin and store into a dump cell), and the
 // prefetch registers alternate by unrolling the plane loop twice instead of being copied.
+constexpr int R2_C2 = 8, R2_C3 = 32, R2_RF2 = 22, R2_RF3 = 72, R2_MAXCH = 64;
+constexpr int R2_FS = R2_RF3 + 1;
 constexpr int R2_MAXJ = 2 * R2_MAXCH + 8;
 
 template <int W, int NPT, int NS>
@@ -515,31 +383,22 @@ __global__ void __launch_bounds__(256, 2) restrict3d_tab_kernel(const TR3 a) {
     }
 }
 
-int g_variant = 3;   // bit 0: table-driven restriction;  bit 1: prolongation with two CTAs per SM
-
 template <int W>
 int launch_prolong(const TR3& a, dim3 grid, cudaStream_t st) {
-    if (g_variant & 2) prolong3d_v2_kernel<W, 2><<<grid, 256, 0, st>>>(a);
-    else prolong3d_v2_kernel<W, 3><<<grid, 256, 0, st>>>(a);
+    prolong3d_v2_kernel<W><<<grid, 256, 0, st>>>(a);
     CHECK_LAUNCH("poms_prolong_3d_v2");
     return 0;
 }
 template <int W, int NS>
-int launch_restrict(const TR3& a, int npt, bool tab, dim3 grid, cudaStream_t st) {
-    if (tab) {
-        if (npt <= 5) restrict3d_tab_kernel<W, 5, NS><<<grid, 256, 0, st>>>(a);
-        else if (npt == 6) restrict3d_tab_kernel<W, 6, NS><<<grid, 256, 0, st>>>(a);
-        else restrict3d_tab_kernel<W, 7, NS><<<grid, 256, 0, st>>>(a);
-    } else if (npt <= 5) restrict3d_v2_kernel<W, 5, NS><<<grid, 256, 0, st>>>(a);
-    else if (npt == 6) restrict3d_v2_kernel<W, 6, NS><<<grid, 256, 0, st>>>(a);
-    else restrict3d_v2_kernel<W, 7, NS><<<grid, 256, 0, st>>>(a);
+int launch_restrict(const TR3& a, int npt, dim3 grid, cudaStream_t st) {
+    if (npt <= 5) restrict3d_tab_kernel<W, 5, NS><<<grid, 256, 0, st>>>(a);
+    else if (npt == 6) restrict3d_tab_kernel<W, 6, NS><<<grid, 256, 0, st>>>(a);
+    else restrict3d_tab_kernel<W, 7, NS><<<grid, 256, 0, st>>>(a);
     CHECK_LAUNCH("poms_restrict_3d_v2");
     return 0;
 }
 
 }  // namespace
-
-extern "C" void poms_set_transfer_variant(int v) { g_variant = v; }
 
 extern "C" int poms_prolong_3d_v2(const double* coarse, double* fine, int n1f, int n2f, int n3f,
                                   int64_t ldf, int64_t pldf, int n1c, int n2c, int n3c, int64_t ldc,
@@ -621,19 +480,20 @@ extern "C" int poms_restrict_3d_v2(const double* fine, double* coarse, int n1f, 
     dim3 grid(g3, g2, (n1c + chunk - 1) / chunk);
     if (grid.y > 65535 || grid.z > 65535) return t_bad_arg(4, "grid too large");
     cudaStream_t st = (cudaStream_t)stream;
-    // table-driven kernel: the fine planes of one chunk must fit its per-plane tables
-    const bool tab = (g_variant & 1) && rows_extent(s1_host, n1c, W1, n1f, chunk, true) <= R2_MAXJ;
+    // the fine planes of one chunk must fit the per-plane tables of the kernel
+    if (rows_extent(s1_host, n1c, W1, n1f, chunk, true) > R2_MAXJ)
+        return t_bad_arg(22, "rows do not fit the fused-transfer tables (use poms_axis_gather)");
 #define POMS_RS_CASE(WW)                                                           \
     case WW:                                                                       \
-        return nopen <= 4 ? launch_restrict<WW, 4>(a, npt, tab, grid, st)               \
-                          : launch_restrict<WW, 6>(a, npt, tab, grid, st);
+        return nopen <= 4 ? launch_restrict<WW, 4>(a, npt, grid, st)               \
+                          : launch_restrict<WW, 6>(a, npt, grid, st);
     switch (W1) {
         POMS_RS_CASE(3)
         POMS_RS_CASE(4)
         POMS_RS_CASE(5)
         POMS_RS_CASE(6)
         default:
-            return nopen <= 4 ? launch_restrict<7, 4>(a, npt, tab, grid, st) : launch_restrict<7, 6>(a, npt, tab, grid, st);
+            return nopen <= 4 ? launch_restrict<7, 4>(a, npt, grid, st) : launch_restrict<7, 6>(a, npt, grid, st);
     }
 #undef POMS_RS_CASE
 }

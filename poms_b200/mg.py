@@ -107,14 +107,16 @@ def _pitch(n):
 def transfer_v2_min():
     """Fine points per rank from which a transfer uses the round-2 one-pass kernels
     (poms_transfer3d_v2.cu), per operation; None = never.  Measured at p = 3
-    (profiles/r02_ab_transfer_v2.txt): the prolongation wins at every size from 131^3 up (515^3: 0.71 ms
-    against 0.96 ms for three per-axis gathers and 1.41 ms for the round-1 one-pass kernel), the
-    restriction only ties (0.66 vs 0.63 ms), so it stays on the gathers unless
-    POMS_B200_TRANSFER_V2=all.  POMS_B200_TRANSFER_V2=0 switches both off."""
-    mode = os.environ.get("POMS_B200_TRANSFER_V2", "prolong")
+    (profiles/r02_ab_transfer_v2.txt), 515^3 / 259^3 / 131^3 fine points:
+      restriction  0.456 / 0.082 / 0.051 ms  (three per-axis gathers 0.63 / 0.109 / 0.080, round-1
+                                              one-pass kernel 0.77 / 0.142 / 0.052)
+      prolongation 0.72 / 0.128 / 0.028 ms   (gathers 0.96 / 0.150 / 0.054, round 1 1.41 / 0.209 / 0.044)
+    POMS_B200_TRANSFER_V2=0 switches them off (round-2 behaviour before these kernels), =prolong
+    keeps the restriction on the gathers."""
+    mode = os.environ.get("POMS_B200_TRANSFER_V2", "all")
     if mode == "0":
         return {"restrict": None, "prolong": None}
-    return {"restrict": 6_000_000 if mode == "all" else None, "prolong": 1_000_000}
+    return {"restrict": None if mode == "prolong" else 6_000_000, "prolong": 1_000_000}
 
 
 def _fused_restrict(ops, fine, shape_f, ld_f, coarse, shape_c, ld_c, v2=False):

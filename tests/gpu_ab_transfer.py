@@ -3,7 +3,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from poms_b200 import bsplines as bs, _lib
+from poms_b200 import bsplines as bs
 from poms_b200.mg import Transfer
 from poms_b200.stencil import StencilVectorSpace, StencilVector
 
@@ -22,12 +22,9 @@ while N >= Nmin:
     rf.data.copy_(torch.randn(Vf.npts, generator=g, dtype=torch.float64, device=dev))
     ec.data.copy_(torch.randn(Vc.npts, generator=g, dtype=torch.float64, device=dev))
     res = {}
-    for fused in (False, True, "v2", "v2-r0"):
-        # "v2-r0": the first version of the round-2 kernels (scatter with per-plane bookkeeping,
-        # prolongation at three CTAs per SM with 20 bytes of spills)
-        _lib.lib().poms_set_transfer_variant(0 if fused == "v2-r0" else 3)
+    for fused in (False, True, "v2"):
         tr.fused, tr.fused_max = fused is True, (10 ** 12 if fused is True else -1)
-        tr.fused_v2, tr.v2_min = fused in ("v2", "v2-r0"), 0
+        tr.fused_v2, tr.v2_min = fused == "v2", 0
         xf.flat.zero_()
         rc = tr.restrict(rf, Vc)
         tr.prolong_add(ec, xf)
@@ -46,12 +43,11 @@ while N >= Nmin:
             ms = e0.elapsed_time(e1) / reps
             nbytes = 8 * ((N + p) ** 3 * (1 if name == "restrict" else 2) + (N // 2 + p) ** 3)
             print("n=%4d %-12s %-8s %8.4f ms  %6.0f GB/s (algorithmic)" % (
-                N + p, name, {False: "per-axis", True: "fused", "v2": "fused-v2", "v2-r0": "v2-first"}[fused], ms,
+                N + p, name, {False: "per-axis", True: "fused", "v2": "fused-v2"}[fused], ms,
                 nbytes / ms * 1e-6), flush=True)
         for op in ("restrict", "prolong"):
-            assert tr._want_fused(Vf.npts, op) == {False: None, True: "v1", "v2": "v2", "v2-r0": "v2"}[fused]
-    _lib.lib().poms_set_transfer_variant(3)
-    for k in (True, "v2", "v2-r0"):
+            assert tr._want_fused(Vf.npts, op) == {False: None, True: "v1", "v2": "v2"}[fused]
+    for k in (True, "v2"):
         dr = (res[k][0] - res[False][0]).abs().max().item() / res[False][0].abs().max().item()
         dp = (res[k][1] - res[False][1]).abs().max().item() / res[False][1].abs().max().item()
         print("   max rel diff %s vs per-axis: restrict %.1e prolong %.1e" % (
