@@ -112,11 +112,14 @@ def transfer_v2_min():
                                               one-pass kernel 0.77 / 0.142 / 0.052)
       prolongation 0.72 / 0.128 / 0.028 ms   (gathers 0.96 / 0.150 / 0.054, round 1 1.41 / 0.209 / 0.044)
     POMS_B200_TRANSFER_V2=0 switches them off (round-2 behaviour before these kernels), =prolong
-    keeps the restriction on the gathers."""
+    keeps the restriction on the gathers; POMS_B200_TRANSFER_V2_MIN=n sets both thresholds (the
+    multi-GPU parity script runs a second time with 0, so that its small grids take these kernels)."""
     mode = os.environ.get("POMS_B200_TRANSFER_V2", "all")
     if mode == "0":
         return {"restrict": None, "prolong": None}
-    return {"restrict": None if mode == "prolong" else 6_000_000, "prolong": 1_000_000}
+    force = os.environ.get("POMS_B200_TRANSFER_V2_MIN")      # tests: one threshold for both
+    lo_r, lo_p = (int(force), int(force)) if force is not None else (6_000_000, 1_000_000)
+    return {"restrict": None if mode == "prolong" else lo_r, "prolong": lo_p}
 
 
 def _fused_restrict(ops, fine, shape_f, ld_f, coarse, shape_c, ld_c, v2=False):

@@ -12,7 +12,10 @@ from conftest import ROOT
 
 
 @pytest.mark.gpu
-def test_slab_partitioned_path_matches_oracle():
+@pytest.mark.parametrize("v2_min", [None, "0"])
+def test_slab_partitioned_path_matches_oracle(v2_min):
+    """v2_min = "0": the round-2 one-pass transfer kernels (poms_transfer3d_v2.cu) also on the small
+    grids of the script (by default they start at 1e6 / 6e6 fine points per rank)."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -21,8 +24,11 @@ def test_slab_partitioned_path_matches_oracle():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
            "--master-addr", "127.0.0.1", "--master-port", "29533",
            os.path.join(ROOT, "tests", "gpu_dist_check.py")]
+    env = dict(os.environ)
+    if v2_min is not None:
+        env["POMS_B200_TRANSFER_V2_MIN"] = v2_min
     r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
-                       timeout=1500)
+                       timeout=1500, env=env)
     print(r.stdout[-6000:])
     assert r.returncode == 0, r.stdout[-3000:]
     assert "ALL OK" in r.stdout
