@@ -618,7 +618,28 @@ class MGHierarchy:
                 ts = knots_to_insert(f["knots"][a], nf, p, c["knots"][a], nc, p)
                 P1s.append(insertion_matrix(ts, nc, p, c["knots"][a]))
             f["P1s"] = P1s
-        self.Ainv_c = np.linalg.inv(self.levels[-1]["A"].tocsr().toarray())
+        # coarsest level: the reference's exact solve (splu(csc_matrix(Ac)).solve,
+        # /root/reference/sources/mg_jac.py:98-99), restated as a dense inverse while that is small.
+        # Above DENSE_COARSE_MAX unknowns (the bench's own C3 hierarchy stops at 35^3 = 42 875: a
+        # 14.7 GB inverse, 13 minutes on 8 cores) the same exact solve goes through the 1-D
+        # generalised eigenpairs K_a Q_a = M_a Q_a L_a, Q_a^T M_a Q_a = I:
+        #   A^-1 = (x)Q_a . diag(1 / (1 + sum_a l_a)) . (x)Q_a^T        (A = sum_a K_a (x) M_others + (x)M)
+        cl = self.levels[-1]
+        if int(np.prod(cl["A"].npts)) <= self.DENSE_COARSE_MAX:
+            self.Ainv_c = np.linalg.inv(cl["A"].tocsr().toarray())
+            self._fd = None
+        else:
+            from scipy.linalg import eigh
+            self.Ainv_c = None
+            Qs, D = [], 1.0
+            for a, (Mb_, Kb_) in enumerate(zip(cl["Mb"], cl["Kb"])):
+                Md, Kd = band_to_dense(Mb_), band_to_dense(Kb_)
+                w, Q = eigh(0.5 * (Kd + Kd.T), 0.5 * (Md + Md.T))
+                Qs.append(Q)
+                shp = [1] * d
+                shp[a] = len(w)
+                D = D + w.reshape(shp)
+            self._fd = (Qs, D)
         for lv in self.levels[:-1]:
             A = lv["A"]
             if smoother == "glt":
@@ -686,10 +707,24 @@ class MGHierarchy:
             x = x + d
         return x
 
+    DENSE_COARSE_MAX = 6000
+
+    def coarse_solve(self, b):
+        if self._fd is None:
+            return (self.Ainv_c @ b.ravel()).reshape(b.shape)
+        Qs, D = self._fd
+        z = b
+        for a, Q in enumerate(Qs):
+            z = np.moveaxis(np.tensordot(Q.T, z, axes=(1, a)), 0, a)
+        z = z / D
+        for a, Q in enumerate(Qs):
+            z = np.moveaxis(np.tensordot(Q, z, axes=(1, a)), 0, a)
+        return z
+
     def vcycle(self, l, b):
         lv = self.levels[l]
         if l == len(self.levels) - 1:
-            return (self.Ainv_c @ b.ravel()).reshape(b.shape)
+            return self.coarse_solve(b)
         x = self.smooth(lv, b, np.zeros_like(b), True)
         r = b - lv["A"].dot(x)
         x = x + prolong(lv["P1s"], self.vcycle(l + 1, restrict(lv["P1s"], r)))

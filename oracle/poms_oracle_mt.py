@@ -219,7 +219,7 @@ class MGHierarchyMT(po.MGHierarchy):
     def vcycle(self, l, b):
         lv = self.levels[l]
         if l == len(self.levels) - 1:
-            return (self.Ainv_c @ b.ravel()).reshape(b.shape)
+            return self.coarse_solve(b)
         nd = b.ndim
         x = self.smooth(lv, b, np.zeros_like(b), True)
         r = b - lv["A"].dot(x)
