@@ -22,7 +22,7 @@ def test_slab_partitioned_path_matches_oracle(v2_min):
         pytest.skip("needs at least 2 GPUs (found %d)" % n)
     n = 8 if n >= 8 else 4 if n >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
-           "--master-addr", "127.0.0.1", "--master-port", "29533",
+           "--master-addr", "127.0.0.1", "--master-port", "29533" if v2_min is None else "29534",
            os.path.join(ROOT, "tests", "gpu_dist_check.py")]
     env = dict(os.environ)
     if v2_min is not None:
