@@ -73,6 +73,38 @@ def test_fused_transfer_checks_rows_against_its_tiles_on_the_host():
     assert L.poms_restrict_3d(None, *args(s_ok, s_ok, s_ok, 5)[1:]) == -1
 
 
+def test_v2_transfer_entries_check_rows_on_the_host():
+    """poms_restrict_3d_v2 / poms_prolong_3d_v2 (big-level one-pass kernels): one row width on all
+    axes, rows inside the tiles, monotone starts -- refused with a negative status before any launch,
+    so that mg.Transfer falls back to the round-1 kernels / the per-axis gathers."""
+    import numpy as np
+    from poms_b200 import bsplines as bs
+    L = _lib.lib()
+    p, Nc = 3, 16
+    st, cf, _ = bs.knot_insertion_rows(bs.make_open_knots(p, Nc + p), bs.make_open_knots(p, 2 * Nc + p), p)
+    stt, cft = bs.rows_transpose(st, cf, Nc + p)
+    sr = np.ascontiguousarray(stt, dtype=np.int32)
+    sp = np.ascontiguousarray(st, dtype=np.int32)
+    nf, nc = 2 * Nc + p, Nc + p
+    dims = (nf, nf, nf, nf + 1, nf * (nf + 1), nc, nc, nc, nc + 1, nc * (nc + 1))
+    WR, WP = cft.shape[1], cf.shape[1]
+    rargs = lambda s1, s2, s3, W1, W2, W3: (1, 1) + dims + (1, 1, W1, 1, 1, W2, 1, 1, W3, s1.ctypes.data,
+                                                          s2.ctypes.data, s3.ctypes.data, None)
+    pargs = lambda s2, s3, W1, W2, W3: (1, 1) + dims + (1, 1, W1, 1, 1, W2, 1, 1, W3, s2.ctypes.data,
+                                                      s3.ctypes.data, 1, None)
+    assert L.poms_restrict_3d_v2(*rargs(sr, sr, sr, WR, WR - 1, WR)) == -15      # mixed widths
+    assert L.poms_restrict_3d_v2(*rargs(sr, sr, sr, 8, 8, 8)) == -15            # wider than 7
+    assert L.poms_prolong_3d_v2(*pargs(sp, sp, WP, WP, WP + 1)) == -15
+    assert b"poms_prolong_3d" in L.poms_last_error()
+    s_bad = np.ascontiguousarray(np.arange(nc) * 8, dtype=np.int32)
+    assert L.poms_restrict_3d_v2(*rargs(sr, s_bad, sr, WR, WR, WR)) == -22      # tile of 8 rows > 22 fine rows
+    assert L.poms_restrict_3d_v2(*rargs(np.ascontiguousarray(sr[::-1]), sr, sr, WR, WR, WR)) == -22
+    s_wide = np.ascontiguousarray(np.arange(nf) * 2, dtype=np.int32)
+    assert L.poms_prolong_3d_v2(*pargs(s_wide, sp, WP, WP, WP)) == -22          # 16 fine rows > 16 coarse rows
+    assert L.poms_prolong_3d_v2(None, *pargs(sp, sp, WP, WP, WP)[1:]) == -1
+    assert L.poms_restrict_3d_v2(1, None, *rargs(sr, sr, sr, WR, WR, WR)[2:]) == -1
+
+
 def test_no_cpu_path():
     import torch
     from poms_b200.stencil import DeviceContext

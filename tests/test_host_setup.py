@@ -400,3 +400,39 @@ def test_bench_hierarchy_layout_per_rank(world):
                 Vc = h.levels[h.levels.index(lv) + 1].V
                 assert ghost_view_range(tr.tc, tr.need_c, rank, Vc.pads[0], Vc.glo, Vc.local_shape[0])
         assert h.levels[-1].V.local_shape[0] == 16 * world + 3
+
+
+def test_transfer_kernel_policy(monkeypatch):
+    """Which transfer kernel a level takes (mg.Transfer._want_fused): round-1 one-pass kernels on the
+    small levels, round-2 one-pass kernels from 1e6 (prolongation) / 6e6 (restriction) fine points
+    per rank, per-axis gathers in 2-D, after a refusal by the C ABI, or when switched off."""
+    torch = pytest.importorskip("torch")
+    from poms_b200 import mg
+    p = 3
+    cpu = torch.device("cpu")
+
+    def make(nd):
+        Tf = [bs.make_open_knots(p, 16 + p)] * nd
+        Tc = [bs.make_open_knots(p, 8 + p)] * nd
+        return mg.Transfer(Tc, Tf, p, cpu)
+
+    for var in ("POMS_B200_TRANSFER_V2", "POMS_B200_TRANSFER_V2_MIN"):
+        monkeypatch.delenv(var, raising=False)
+    tr = make(3)
+    assert [tr._want_fused((n,) * 3, "restrict") for n in (35, 131, 259, 515)] == ["v1", "v1", "v2", "v2"]
+    assert [tr._want_fused((n,) * 3, "prolong") for n in (35, 67, 131, 515)] == ["v1", "v1", "v2", "v2"]
+    tr._fused_failed("v2")                       # the C ABI refused the rows once: never asked again
+    assert tr._want_fused((515,) * 3, "restrict") is None and tr._want_fused((131,) * 3, "prolong") == "v1"
+    tr._fused_failed("v1")
+    assert tr._want_fused((35,) * 3, "restrict") is None
+    assert make(2)._want_fused((2051, 2051), "restrict") is None
+    monkeypatch.setenv("POMS_B200_TRANSFER_V2", "0")
+    tr = make(3)
+    assert tr._want_fused((515,) * 3, "prolong") is None and tr._want_fused((131,) * 3, "prolong") == "v1"
+    monkeypatch.setenv("POMS_B200_TRANSFER_V2", "prolong")
+    tr = make(3)
+    assert tr._want_fused((515,) * 3, "restrict") is None and tr._want_fused((515,) * 3, "prolong") == "v2"
+    monkeypatch.setenv("POMS_B200_TRANSFER_V2", "all")
+    monkeypatch.setenv("POMS_B200_TRANSFER_V2_MIN", "0")
+    tr = make(3)
+    assert tr._want_fused((19,) * 3, "restrict") == tr._want_fused((19,) * 3, "prolong") == "v2"
