@@ -775,10 +775,10 @@ def vcycle(h, l, b, final_dot=None):
     h.smooth(lv, b, x, True)
     r = lv.ws("r")
     lv.A.apply(x, r, EPI_RESID, b=b)
-    with profiling.region("restrict", 8 * lv.V.local_size, launches=h.ndim):
+    with profiling.region("restrict", 8 * lv.V.local_size, launches=None):
         rc = lv.transfer.restrict(r, h.levels[l + 1].V, out=h.levels[l + 1].ws("b"))
     ec = vcycle(h, l + 1, rc)
-    with profiling.region("prolong_add", 16 * lv.V.local_size, launches=h.ndim):
+    with profiling.region("prolong_add", 16 * lv.V.local_size, launches=None):
         lv.transfer.prolong_add(ec, x)
     h.smooth(lv, b, x, False, final_dot=final_dot)
     return x

@@ -24,14 +24,22 @@ def enabled():
 
 @contextlib.contextmanager
 def region(name, nbytes=0, launches=1):
+    """launches=None: counted from the library's own launch counter (regions whose number of kernels
+    depends on the path taken, e.g. one-pass or per-axis transfers)."""
     if not _enabled:
         yield
         return
     a = torch.cuda.Event(enable_timing=True)
     b = torch.cuda.Event(enable_timing=True)
+    n0 = 0
+    if launches is None:
+        from . import _lib
+        n0 = _lib.lib().poms_launch_count()
     a.record()
     yield
     b.record()
+    if launches is None:
+        launches = _lib.lib().poms_launch_count() - n0
     _records.append((name, a, b, int(nbytes), int(launches)))
 
 
