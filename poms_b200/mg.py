@@ -17,9 +17,8 @@ EXTENSION beyond the reference (labelled in every report
     /root/reference/slides/content.tex:141-153) -- because a fixed SPD preconditioner is what CG
     needs (the reference's omega = 2/3 Jacobi diverges for p >= 3).
 """
-from math import sqrt
-
 import os
+from math import sqrt
 
 import numpy as np
 import torch
