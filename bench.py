@@ -488,6 +488,15 @@ def main():
                                   "avg_launch_ms": kf["ms"] / kf["launches"],
                                   "share_of_step": kf["ms"] / (ms * steps) if ms > 0 else 0.0}
     ms = ms_headline
+    # which transfer kernel every level pair takes (mg.Transfer._want_fused): "v2" = one-pass kernels of
+    # poms_transfer3d_v2.cu, "v1" = round-1 one-pass kernels, None = per-axis gathers
+    try:
+        transfer_note = [{"fine_points_per_gpu": int(np.prod(l.V.local_shape)),
+                          "restrict": l.transfer._want_fused(l.V.local_shape, "restrict"),
+                          "prolong": l.transfer._want_fused(l.V.local_shape, "prolong")}
+                         for l in h.levels[:-1]]
+    except Exception as exc:                     # informational only
+        transfer_note = "n/a: %r" % (exc,)
     line = {
         "metric": METRIC, "value": dof_global / (ms * 1e-3), "unit": "DOF/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -511,6 +520,7 @@ def main():
                    "coarsest_elements": Nc,
                    "iterations": info["niter"], "restarts": info.get("restarts", 0),
                    "levels": len(h.levels),
+                   "transfer_kernels": transfer_note,
                    "rel_residual_reported": info["res_norm"] / info["res_norm0"],
                    "rel_residual_true": true_rel,
                    "l2_note": "vectors are %.0f MB each, larger than the 126 MB L2"
