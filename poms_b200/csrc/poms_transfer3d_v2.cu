@@ -19,9 +19,19 @@
 //   * the row width W is a template parameter and the tap loops carry no bounds checks: the tile
 //     buffers are zero-initialised with a pad row, so a tap that leaves the tile meets a finite value
 //     and, by the row format, a zero coefficient.
-#include <string.h>
+//
+// POMS_HOST_EMU is never defined by build.py: libpoms_b200.so contains the CUDA kernels only.  The
+// CPU test tests/test_kernel_host_emulation.py defines it to compile THIS file for the host over
+// tests/host_emu/cuda_emu.h (one OS thread per CUDA thread, a pthread barrier for __syncthreads) under
+// AddressSanitizer and ThreadSanitizer: out-of-bounds accesses and missing barriers of the kernels
+// below show up without a GPU, on every row width and on ragged / slab-plan shapes.
+#ifdef POMS_HOST_EMU
+#include "cuda_emu.h"
+#else
 #define POMS_TU 99
 #include "poms_kernels.cu"
+#define POMS_LAUNCH(kernel, grid, stream, arg) kernel<<<grid, 256, 0, stream>>>(arg)
+#endif
 
 namespace {
 
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(256, 3) prolong3d_v2_kernel(const TR3 a) {
 // CTA first tabulate, per fine plane j of its chunk, the first open coarse row
 // base(j), the weights of j in rows base(j) .. base(j)+NS-1 (zero where j is outside the row) and the
 // number of rows that end at j; the march is then branch-free: NS broadcast weights x NPT FMAs per
-// plane, unpredicated loads (dead slots re-read the tile origin and store into a dump cell), and the
+// plane, unpredicated loads (dead slots re-read the tile origin; only their shared-memory store is masked), and the
 // prefetch registers alternate by unrolling the plane loop twice instead of being copied.
 constexpr int R2_C2 = 8, R2_C3 = 32, R2_RF2 = 22, R2_RF3 = 72, R2_MAXCH = 64;
 constexpr int R2_FS = R2_RF3 + 1;
@@ -275,15 +285,17 @@ __global__ void __launch_bounds__(256, 2) restrict3d_tab_kernel(const TR3 a) {
     const int o3 = v3 ? a.s3[c3_0 + tx] - f3lo : 0;
     const int o2 = v2 ? a.s2[c2_0 + ty] - f2lo : 0;
     // this thread's points of the halo'd fine tile (row-major over its true extent nf2 x nf3); dead
-    // slots read the tile origin and write the last cell of the pad row, which no tap reaches
+    // slots re-read the tile origin (unpredicated loads) and are masked out of the shared-memory store
     int go[NPT], so[NPT];
+    unsigned fmask = 0;
 #pragma unroll
     for (int m = 0; m < NPT; ++m) {
         const int slot = tid + 256 * m;
         const int r = slot / nf3, c = slot - r * nf3;
         const bool ok = r < nf2;
+        if (ok) fmask |= 1u << m;
         go[m] = ok ? (int)((int64_t)r * a.ldf) + c : 0;
-        so[m] = ok ? r * R2_FS + c : (R2_RF2 + 1) * R2_FS - 1;
+        so[m] = ok ? r * R2_FS + c : 0;
     }
     __syncthreads();
 
@@ -346,7 +358,8 @@ __global__ void __launch_bounds__(256, 2) restrict3d_tab_kernel(const TR3 a) {
 #pragma unroll 1
         for (int e = 0; e < ne; ++e) {
 #pragma unroll
-            for (int m = 0; m < NPT; ++m) F[so[m]] = acc[0][m];
+            for (int m = 0; m < NPT; ++m)
+                if (fmask >> m & 1u) F[so[m]] = acc[0][m];
             __syncthreads();
             if (v3) {
 #pragma unroll 1
@@ -385,15 +398,15 @@ __global__ void __launch_bounds__(256, 2) restrict3d_tab_kernel(const TR3 a) {
 
 template <int W>
 int launch_prolong(const TR3& a, dim3 grid, cudaStream_t st) {
-    prolong3d_v2_kernel<W><<<grid, 256, 0, st>>>(a);
+    POMS_LAUNCH(prolong3d_v2_kernel<W>, grid, st, a);
     CHECK_LAUNCH("poms_prolong_3d_v2");
     return 0;
 }
 template <int W, int NS>
 int launch_restrict(const TR3& a, int npt, dim3 grid, cudaStream_t st) {
-    if (npt <= 5) restrict3d_tab_kernel<W, 5, NS><<<grid, 256, 0, st>>>(a);
-    else if (npt == 6) restrict3d_tab_kernel<W, 6, NS><<<grid, 256, 0, st>>>(a);
-    else restrict3d_tab_kernel<W, 7, NS><<<grid, 256, 0, st>>>(a);
+    if (npt <= 5) POMS_LAUNCH((restrict3d_tab_kernel<W, 5, NS>), grid, st, a);
+    else if (npt == 6) POMS_LAUNCH((restrict3d_tab_kernel<W, 6, NS>), grid, st, a);
+    else POMS_LAUNCH((restrict3d_tab_kernel<W, 7, NS>), grid, st, a);
     CHECK_LAUNCH("poms_restrict_3d_v2");
     return 0;
 }

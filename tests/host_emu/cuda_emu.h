@@ -1,0 +1,68 @@
+// cuda_emu.h -- TEST INFRASTRUCTURE ONLY: just enough of the CUDA execution model to compile a kernel
+// source file for the HOST (tests/test_kernel_host_emulation.py): one OS thread per CUDA thread of a
+// block, blocks one after the other, __syncthreads() = pthread barrier, __shared__ = function-local
+// static.  Built with -fsanitize=address or -fsanitize=thread, so that out-of-bounds accesses and
+// missing barriers of the kernel show up on a machine without a GPU.  Never part of libpoms_b200.so.
+#pragma once
+#include <pthread.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct emu_idx {
+    unsigned x, y, z;
+};
+static thread_local emu_idx threadIdx, blockIdx;
+static pthread_barrier_t emu_bar;
+static inline void __syncthreads() { pthread_barrier_wait(&emu_bar); }
+typedef void* cudaStream_t;
+static char g_err[256];
+static long long g_launches;
+
+#define __global__
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __host__
+#define __device__
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
+template <class T>
+static inline T __ldcs(const T* p) { return *p; }
+using std::max;
+using std::min;
+
+#define CHECK_LAUNCH(where) \
+    do {                    \
+        g_launches++;       \
+    } while (0)
+#define POMS_LAUNCH(kernel, grid, stream, arg) emu_launch(grid, [&] { kernel(arg); })
+
+constexpr int EMU_BLOCK = 256;
+template <class F>
+static void emu_launch(dim3 grid, F body) {
+    pthread_barrier_init(&emu_bar, nullptr, EMU_BLOCK);
+    std::vector<std::thread> th;
+    th.reserve(EMU_BLOCK);
+    for (int t = 0; t < EMU_BLOCK; ++t)
+        th.emplace_back([&, t] {
+            threadIdx = {(unsigned)t, 0u, 0u};
+            for (unsigned z = 0; z < grid.z; ++z)
+                for (unsigned y = 0; y < grid.y; ++y)
+                    for (unsigned x = 0; x < grid.x; ++x) {
+                        blockIdx = {x, y, z};
+                        body();
+                        pthread_barrier_wait(&emu_bar);   // the next block reuses the "shared" statics
+                    }
+        });
+    for (auto& x : th) x.join();
+    pthread_barrier_destroy(&emu_bar);
+}

@@ -1,0 +1,135 @@
+"""The CUDA source of the one-pass transfer kernels (poms_b200/csrc/poms_transfer3d_v2.cu), compiled for
+the HOST over tests/host_emu/cuda_emu.h (one OS thread per CUDA thread, pthread barrier =
+__syncthreads, function-local statics = shared memory) and run under AddressSanitizer and
+ThreadSanitizer through the file's own C entry points (host checks, chunking and template dispatch
+included).  What this catches without a GPU: out-of-bounds global / shared accesses (every array is an
+exactly sized heap block), missing or misplaced barriers (data races between the emulated threads),
+and wrong results, on every row width p = 1..5, ragged tiles and the row tables of a slab plan
+(starts relative to a rank's plane block, also negative).  TEST INFRASTRUCTURE: libpoms_b200.so never
+contains this build (POMS_HOST_EMU is not defined by build.py), and timing it means nothing."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import poms_oracle as po
+from poms_b200 import bsplines as bs
+
+EMU = os.path.join(ROOT, "tests", "host_emu")
+
+
+@pytest.fixture(scope="module")
+def exes(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    d = tmp_path_factory.mktemp("emu")
+    procs = {}
+    for name, flags in (("asan", ["-fsanitize=address", "-fno-omit-frame-pointer"]), ("tsan", ["-fsanitize=thread"])):
+        out = str(d / ("emu_" + name))
+        procs[name] = (out, subprocess.Popen(
+            [gxx, "-std=c++17", "-O1", "-g"] + flags + ["-I" + EMU, os.path.join(EMU, "emu_transfer.cpp"),
+                                                         "-o", out, "-lpthread"],
+            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    res = {}
+    for name, (out, pr) in procs.items():
+        log = pr.communicate()[0]
+        assert pr.returncode == 0, log[-3000:]
+        res[name] = out
+    return res
+
+
+def _pitch(n):
+    return n + (n & 1)
+
+
+def _run(exe, tmp, op, rows, src, dst, nf, nc):
+    """op 0: dst(coarse) = R src(fine);  op 1: dst(fine) += P src(coarse).  rows: [(start, coef)] * 3."""
+    ldf, ldc = _pitch(nf[2]), _pitch(nc[2])
+
+    def pitched(a, ld):
+        t = np.zeros(a.shape[:2] + (ld,))
+        t[:, :, :a.shape[2]] = a
+        return t
+
+    hdr = np.array([op, *nf, *nc, *[r[1].shape[1] for r in rows], 1, ldf, ldc, *[len(r[0]) for r in rows]],
+                   dtype=np.int32)
+    fi, fo = str(tmp / "in.bin"), str(tmp / "out.bin")
+    with open(fi, "wb") as f:
+        hdr.tofile(f)
+        for s, c in rows:
+            np.ascontiguousarray(s, dtype=np.int32).tofile(f)
+            np.ascontiguousarray(c, dtype=np.float64).tofile(f)
+        pitched(src, ldf if op == 0 else ldc).tofile(f)
+        pitched(dst, ldc if op == 0 else ldf).tofile(f)
+    env = dict(os.environ, TSAN_OPTIONS="exitcode=66", ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([exe, fi, fo], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and not r.stderr.strip(), (r.returncode, r.stderr[-4000:])
+    raw = open(fo, "rb").read()
+    assert np.frombuffer(raw[:4], dtype=np.int32)[0] == 0
+    shp, ld = (nc, ldc) if op == 0 else (nf, ldf)
+    out = np.frombuffer(raw[4:], dtype=np.float64).reshape(shp[0], shp[1], ld)
+    assert not out[:, :, shp[2]:].any()            # the pad column stays zero
+    return out[:, :, :shp[2]]
+
+
+def _tables(p, N):
+    Nc = [n // 2 for n in N]
+    nf, nc = [n + p for n in N], [n + p for n in Nc]
+    P, R, P1s = [], [], []
+    for a in range(3):
+        Tf, Tc = bs.make_open_knots(p, nf[a]), bs.make_open_knots(p, nc[a])
+        st, cf, _ = bs.knot_insertion_rows(Tc, Tf, p)
+        stt, cft = bs.rows_transpose(st, cf, nc[a])
+        P.append((st, cf))
+        R.append((stt, cft))
+        ts = po.knots_to_insert(Tf, nf[a], p, Tc, nc[a], p)
+        P1s.append(po.insertion_matrix(ts, nc[a], p, Tc))
+    return nf, nc, P, R, P1s
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+CASES = [(3, (20, 36, 140)), (1, (8, 8, 16)), (2, (36, 18, 130)), (5, (12, 44, 72)), (4, (16, 20, 70)),
+         (3, (130, 16, 16))]
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("p,N", CASES)
+def test_transfer_kernels_emulated(exes, tmp_path, san, p, N):
+    if san == "tsan" and max(N) > 100 and p != 3:
+        pytest.skip("the thread sanitizer runs one long-axis case per kernel family")
+    nf, nc, P, R, P1s = _tables(p, N)
+    rng = np.random.default_rng(1)
+    rf, ec, xf = rng.standard_normal(nf), rng.standard_normal(nc), rng.standard_normal(nf)
+    assert rel(_run(exes[san], tmp_path, 0, R, rf, np.zeros(nc), nf, nc), po.restrict(P1s, rf)) < 1e-14
+    assert rel(_run(exes[san], tmp_path, 1, P, ec, xf, nf, nc), xf + po.prolong(P1s, ec)) < 1e-14
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("p,N,size", [(3, (48, 20, 70), 2), (2, (40, 36, 24), 3)])
+def test_transfer_kernels_emulated_on_slab_plan_rows(exes, tmp_path, san, p, N, size):
+    from poms_b200.dist import slab_transfer_plan
+    nf, nc, P, R, P1s = _tables(p, N)
+    rng = np.random.default_rng(5)
+    rf, ec, xf = rng.standard_normal(nf), rng.standard_normal(nc), rng.standard_normal(nf)
+    rc_ref, xf_ref = po.restrict(P1s, rf), xf + po.prolong(P1s, ec)
+    plan = slab_transfer_plan(P[0][0], P[0][1], nc[0], size, True)
+    assert min(pl[0].min() for pl in plan["P0"]) < 0        # the case the kernels clamp
+    for q in range(size):
+        (fs, fe), (cs, ce) = plan["tf"][q], plan["tc"][q]
+        lo, hi = plan["need_f"][q]
+        s0, c0, _ = plan["R0"][q]
+        out = _run(exes[san], tmp_path, 0, [(s0, c0), R[1], R[2]], rf[lo:hi + 1],
+                   np.zeros((ce - cs + 1, nc[1], nc[2])), (hi - lo + 1, nf[1], nf[2]), (ce - cs + 1, nc[1], nc[2]))
+        assert rel(out, rc_ref[cs:ce + 1]) < 1e-14
+        lo, hi = plan["need_c"][q]
+        s0, c0, _ = plan["P0"][q]
+        out = _run(exes[san], tmp_path, 1, [(s0, c0), P[1], P[2]], ec[lo:hi + 1], xf[fs:fe + 1],
+                   (fe - fs + 1, nf[1], nf[2]), (hi - lo + 1, nc[1], nc[2]))
+        assert rel(out, xf_ref[fs:fe + 1]) < 1e-14
