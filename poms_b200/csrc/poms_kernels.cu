@@ -47,6 +47,9 @@ extern POMS_HIDDEN int64_t g_launches;
         cudaError_t e_ = cudaGetLastError();                    \
         if (e_ != cudaSuccess) return fail_cuda(e_, where);     \
     } while (0)
+// launch of a 256-thread kernel with one struct argument; tests/host_emu redefines it to run the
+// kernel source on the host under sanitizers (POMS_HOST_EMU, never defined by build.py)
+#define POMS_LAUNCH(kernel, grid, stream, arg) kernel<<<grid, 256, 0, stream>>>(arg)
 
 #if POMS_TU == 0
 extern "C" int poms_version(void) { return 100; }

@@ -85,6 +85,9 @@ __global__ void __launch_bounds__(256, 4) prolong3d_kernel(const PR3 a) {
             xo[q] = (a.accumulate && v3 && r < f2l) ? __ldcs(dst + (int64_t)r * a.ldf) : 0.0;
         }
         // ---- G: axis-1 combination of the coarse planes, on the coarse tile (independent loads) ----
+        // (plane index clamped on BOTH sides: the rows of a slab plan may start before the plane block,
+        // dist.slab_transfer_plan; those taps carry zero coefficients.  The lower clamp was missing until
+        // tests/test_kernel_host_emulation.py ran this kernel under AddressSanitizer)
         const int p0 = s1s[j1 - j_lo];
         double w1[PR_WMAX];
 #pragma unroll
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(256, 4) prolong3d_kernel(const PR3 a) {
                 double gv[PR_WMAX];
 #pragma unroll
                 for (int k = 0; k < PR_WMAX; ++k)
-                    gv[k] = k < a.W1 ? __ldg(gsrc[q] + (int64_t)min(p0 + k, a.n1c - 1) * a.pldc) : 0.0;
+                    gv[k] = k < a.W1 ? __ldg(gsrc[q] + (int64_t)max(0, min(p0 + k, a.n1c - 1)) * a.pldc) : 0.0;
                 double gsum = 0.0;
 #pragma unroll
                 for (int k = 0; k < PR_WMAX; ++k) gsum = fma(w1[k], gv[k], gsum);
@@ -294,7 +297,7 @@ extern "C" int poms_prolong_3d(const double* coarse, double* fine, int n1f, int 
     a.chunk = chunk;
     dim3 grid(g3, g2, (n1f + chunk - 1) / chunk);
     if (grid.y > 65535 || grid.z > 65535) return bad_arg(4, "grid too large");
-    prolong3d_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    POMS_LAUNCH(prolong3d_kernel, grid, (cudaStream_t)stream, a);
     CHECK_LAUNCH("poms_prolong_3d");
     return 0;
 }
@@ -329,7 +332,7 @@ extern "C" int poms_restrict_3d(const double* fine, double* coarse, int n1f, int
     a.chunk = chunk;
     dim3 grid(g3, g2, (n1c + chunk - 1) / chunk);
     if (grid.y > 65535 || grid.z > 65535) return bad_arg(4, "grid too large");
-    restrict3d_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    POMS_LAUNCH(restrict3d_kernel, grid, (cudaStream_t)stream, a);
     CHECK_LAUNCH("poms_restrict_3d");
     return 0;
 }

@@ -30,7 +30,6 @@
 #else
 #define POMS_TU 99
 #include "poms_kernels.cu"
-#define POMS_LAUNCH(kernel, grid, stream, arg) kernel<<<grid, 256, 0, stream>>>(arg)
 #endif
 
 namespace {

@@ -40,6 +40,17 @@ static inline T __ldcs(const T* p) { return *p; }
 using std::max;
 using std::min;
 
+// cp.async (8 bytes per thread): the copy happens at once, commit / wait are no-ops -- a missing wait is
+// therefore NOT something this emulation can see
+static inline void cp_async8(void* smem, const void* gmem) { memcpy(smem, gmem, 8); }
+static inline void cp_async_commit() {}
+template <int N>
+static inline void cp_async_wait() {}
+[[maybe_unused]] static int bad_arg(int idx, const char* what) {
+    snprintf(g_err, sizeof(g_err), "bad argument %d: %s", idx, what);
+    return -idx;
+}
+
 #define CHECK_LAUNCH(where) \
     do {                    \
         g_launches++;       \

@@ -3,12 +3,14 @@
 // from a file.  Every array is copied into an exactly sized heap block, so that AddressSanitizer sees
 // any access outside it.
 //   emu_transfer <in> <out>
-// in:  int32 header {op (0 restrict, 1 prolong), n1f, n2f, n3f, n1c, n2c, n3c, W1, W2, W3, accumulate,
+// in:  int32 header {op (0 restrict, 1 prolong: poms_*_3d_v2; 2, 3: the round-1 kernels poms_restrict_3d /
+//      poms_prolong_3d of poms_transfer3d.cuh), n1f, n2f, n3f, n1c, n2c, n3c, W1, W2, W3, accumulate,
 //      ldf, ldc, rows1, rows2, rows3}, then per axis starts (rows int32) and coefficients (rows * W
 //      fp64), then the source array and the destination array (pitched, fp64).
 // out: int32 status, then the destination array.
 #define POMS_HOST_EMU 1
 #include "../../poms_b200/csrc/poms_transfer3d_v2.cu"
+#include "../../poms_b200/csrc/poms_transfer3d.cuh"
 
 #include <cstdlib>
 #include <memory>
@@ -28,7 +30,7 @@ int main(int argc, char** argv) {
     FILE* f = fopen(argv[1], "rb");
     if (!f) return 2;
     auto h = rd<int32_t>(f, 16);
-    const int op = h[0], n1f = h[1], n2f = h[2], n3f = h[3], n1c = h[4], n2c = h[5], n3c = h[6];
+    const int opx = h[0], op = opx & 1, n1f = h[1], n2f = h[2], n3f = h[3], n1c = h[4], n2c = h[5], n3c = h[6];
     const int W[3] = {h[7], h[8], h[9]}, accumulate = h[10], ldf = h[11], ldc = h[12];
     const int rows[3] = {h[13], h[14], h[15]};
     std::unique_ptr<int32_t[]> s[3];
@@ -42,7 +44,15 @@ int main(int argc, char** argv) {
     auto dst = rd<double>(f, op == 0 ? ncoarse : nfine);
     fclose(f);
     int rc;
-    if (op == 0)
+    if (opx == 2)
+        rc = poms_restrict_3d(src.get(), dst.get(), n1f, n2f, n3f, ldf, (int64_t)n2f * ldf, n1c, n2c, n3c, ldc,
+                              (int64_t)n2c * ldc, s[0].get(), c[0].get(), W[0], s[1].get(), c[1].get(), W[1],
+                              s[2].get(), c[2].get(), W[2], s[0].get(), s[1].get(), s[2].get(), nullptr);
+    else if (opx == 3)
+        rc = poms_prolong_3d(src.get(), dst.get(), n1f, n2f, n3f, ldf, (int64_t)n2f * ldf, n1c, n2c, n3c, ldc,
+                             (int64_t)n2c * ldc, s[0].get(), c[0].get(), W[0], s[1].get(), c[1].get(), W[1],
+                             s[2].get(), c[2].get(), W[2], s[1].get(), s[2].get(), accumulate, nullptr);
+    else if (op == 0)
         rc = poms_restrict_3d_v2(src.get(), dst.get(), n1f, n2f, n3f, ldf, (int64_t)n2f * ldf, n1c, n2c, n3c,
                                  ldc, (int64_t)n2c * ldc, s[0].get(), c[0].get(), W[0], s[1].get(),
                                  c[1].get(), W[1], s[2].get(), c[2].get(), W[2], s[0].get(), s[1].get(),

@@ -1,5 +1,5 @@
-"""The CUDA source of the one-pass transfer kernels (poms_b200/csrc/poms_transfer3d_v2.cu), compiled for
-the HOST over tests/host_emu/cuda_emu.h (one OS thread per CUDA thread, pthread barrier =
+"""The CUDA source of the one-pass transfer kernels (poms_b200/csrc/poms_transfer3d_v2.cu and the round-1
+kernels of poms_transfer3d.cuh), compiled for the HOST over tests/host_emu/cuda_emu.h (one OS thread per CUDA thread, pthread barrier =
 __syncthreads, function-local statics = shared memory) and run under AddressSanitizer and
 ThreadSanitizer through the file's own C entry points (host checks, chunking and template dispatch
 included).  What this catches without a GPU: out-of-bounds global / shared accesses (every array is an
@@ -47,7 +47,9 @@ def _pitch(n):
 
 
 def _run(exe, tmp, op, rows, src, dst, nf, nc):
-    """op 0: dst(coarse) = R src(fine);  op 1: dst(fine) += P src(coarse).  rows: [(start, coef)] * 3."""
+    """op 0: dst(coarse) = R src(fine);  op 1: dst(fine) += P src(coarse)  (round-2 kernels; 2, 3: the
+    round-1 kernels).  rows: [(start, coef)] * 3."""
+    opx, op = op, op & 1
     ldf, ldc = _pitch(nf[2]), _pitch(nc[2])
 
     def pitched(a, ld):
@@ -55,7 +57,7 @@ def _run(exe, tmp, op, rows, src, dst, nf, nc):
         t[:, :, :a.shape[2]] = a
         return t
 
-    hdr = np.array([op, *nf, *nc, *[r[1].shape[1] for r in rows], 1, ldf, ldc, *[len(r[0]) for r in rows]],
+    hdr = np.array([opx, *nf, *nc, *[r[1].shape[1] for r in rows], 1, ldf, ldc, *[len(r[0]) for r in rows]],
                    dtype=np.int32)
     fi, fo = str(tmp / "in.bin"), str(tmp / "out.bin")
     with open(fi, "wb") as f:
@@ -99,22 +101,32 @@ CASES = [(3, (20, 36, 140)), (1, (8, 8, 16)), (2, (36, 18, 130)), (5, (12, 44, 7
          (3, (130, 16, 16))]
 
 
+GEN = {"round2": 0, "round1": 2}
+
+
+@pytest.mark.parametrize("gen", ["round2", "round1"])
 @pytest.mark.parametrize("san", ["asan", "tsan"])
 @pytest.mark.parametrize("p,N", CASES)
-def test_transfer_kernels_emulated(exes, tmp_path, san, p, N):
+def test_transfer_kernels_emulated(exes, tmp_path, san, p, N, gen):
     if san == "tsan" and max(N) > 100 and p != 3:
         pytest.skip("the thread sanitizer runs one long-axis case per kernel family")
+    op0 = GEN[gen]
     nf, nc, P, R, P1s = _tables(p, N)
     rng = np.random.default_rng(1)
     rf, ec, xf = rng.standard_normal(nf), rng.standard_normal(nc), rng.standard_normal(nf)
-    assert rel(_run(exes[san], tmp_path, 0, R, rf, np.zeros(nc), nf, nc), po.restrict(P1s, rf)) < 1e-14
-    assert rel(_run(exes[san], tmp_path, 1, P, ec, xf, nf, nc), xf + po.prolong(P1s, ec)) < 1e-14
+    assert rel(_run(exes[san], tmp_path, op0, R, rf, np.zeros(nc), nf, nc), po.restrict(P1s, rf)) < 1e-14
+    assert rel(_run(exes[san], tmp_path, op0 + 1, P, ec, xf, nf, nc), xf + po.prolong(P1s, ec)) < 1e-14
 
 
+@pytest.mark.parametrize("gen", ["round2", "round1"])
 @pytest.mark.parametrize("san", ["asan", "tsan"])
 @pytest.mark.parametrize("p,N,size", [(3, (48, 20, 70), 2), (2, (40, 36, 24), 3)])
-def test_transfer_kernels_emulated_on_slab_plan_rows(exes, tmp_path, san, p, N, size):
+def test_transfer_kernels_emulated_on_slab_plan_rows(exes, tmp_path, san, p, N, size, gen):
+    """Rows of dist.slab_transfer_plan: starts relative to a rank's plane block; the prolongation rows
+    of the inner ranks start BEFORE the block (leading zero coefficients).  The round-1 prolongation
+    kernel read those planes out of bounds until this test ran it under AddressSanitizer."""
     from poms_b200.dist import slab_transfer_plan
+    op0 = GEN[gen]
     nf, nc, P, R, P1s = _tables(p, N)
     rng = np.random.default_rng(5)
     rf, ec, xf = rng.standard_normal(nf), rng.standard_normal(nc), rng.standard_normal(nf)
@@ -125,11 +137,11 @@ def test_transfer_kernels_emulated_on_slab_plan_rows(exes, tmp_path, san, p, N, 
         (fs, fe), (cs, ce) = plan["tf"][q], plan["tc"][q]
         lo, hi = plan["need_f"][q]
         s0, c0, _ = plan["R0"][q]
-        out = _run(exes[san], tmp_path, 0, [(s0, c0), R[1], R[2]], rf[lo:hi + 1],
+        out = _run(exes[san], tmp_path, op0, [(s0, c0), R[1], R[2]], rf[lo:hi + 1],
                    np.zeros((ce - cs + 1, nc[1], nc[2])), (hi - lo + 1, nf[1], nf[2]), (ce - cs + 1, nc[1], nc[2]))
         assert rel(out, rc_ref[cs:ce + 1]) < 1e-14
         lo, hi = plan["need_c"][q]
         s0, c0, _ = plan["P0"][q]
-        out = _run(exes[san], tmp_path, 1, [(s0, c0), P[1], P[2]], ec[lo:hi + 1], xf[fs:fe + 1],
+        out = _run(exes[san], tmp_path, op0 + 1, [(s0, c0), P[1], P[2]], ec[lo:hi + 1], xf[fs:fe + 1],
                    (fe - fs + 1, nf[1], nf[2]), (hi - lo + 1, nc[1], nc[2]))
         assert rel(out, xf_ref[fs:fe + 1]) < 1e-14
