@@ -22,9 +22,17 @@ struct emu_idx {
     unsigned x, y, z;
 };
 static thread_local emu_idx threadIdx, blockIdx;
+static dim3 blockDim, gridDim;
 static pthread_barrier_t emu_bar;
+static pthread_barrier_t emu_warp_bar[32];      // __syncwarp(): one barrier per warp of the block
 static inline void __syncthreads() { pthread_barrier_wait(&emu_bar); }
+static inline void __syncwarp() { pthread_barrier_wait(&emu_warp_bar[threadIdx.x >> 5]); }
 typedef void* cudaStream_t;
+typedef int cudaError_t;
+constexpr int cudaSuccess = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8;
+template <class K>
+static inline int cudaFuncSetAttribute(K, int, int) { return 0; }
+constexpr int EMU_DYN_SMEM_DOUBLES = 28 * 1024;   // 224 KB, the most a kernel can ask for
 static char g_err[256];
 static long long g_launches;
 
@@ -37,6 +45,9 @@ template <class T>
 static inline T __ldg(const T* p) { return *p; }
 template <class T>
 static inline T __ldcs(const T* p) { return *p; }
+// round-to-nearest arithmetic that the compiler must not contract into an FMA
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 using std::max;
 using std::min;
 
@@ -57,9 +68,20 @@ static inline void cp_async_wait() {}
     } while (0)
 #define POMS_LAUNCH(kernel, grid, stream, arg) emu_launch(grid, [&] { kernel(arg); })
 
+// launch with an explicit block size and argument list (sources rewritten by make_emu_source.py)
+#define EMU_LAUNCH_EX(kernel, grid, block, smem, stream, ...) \
+    emu_launch(dim3(grid), [&] { kernel(__VA_ARGS__); }, block)
+
 constexpr int EMU_BLOCK = 256;
 template <class F>
-static void emu_launch(dim3 grid, F body) {
+static void emu_launch(dim3 grid, F body, int nthreads = EMU_BLOCK) {
+    const int EMU_BLOCK = nthreads;               // (shadows the default: the code below is unchanged)
+    blockDim = dim3(nthreads);
+    gridDim = grid;
+    // a warp whose threads all leave the kernel early must not block the others: the block barrier
+    // is only used by kernels that keep every thread (checked by the kernels' own structure)
+    for (int w = 0; w < (nthreads + 31) / 32; ++w)
+        pthread_barrier_init(&emu_warp_bar[w], nullptr, std::min(32, nthreads - 32 * w));
     pthread_barrier_init(&emu_bar, nullptr, EMU_BLOCK);
     std::vector<std::thread> th;
     th.reserve(EMU_BLOCK);
@@ -76,4 +98,5 @@ static void emu_launch(dim3 grid, F body) {
         });
     for (auto& x : th) x.join();
     pthread_barrier_destroy(&emu_bar);
+    for (int w = 0; w < (nthreads + 31) / 32; ++w) pthread_barrier_destroy(&emu_warp_bar[w]);
 }

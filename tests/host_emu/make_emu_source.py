@@ -1,0 +1,40 @@
+"""TEST INFRASTRUCTURE ONLY: cut a kernel section out of poms_b200/csrc/poms_kernels.cu and rewrite the
+CUDA-only syntax so that g++ can compile it over cuda_emu.h:
+    kernel<T...><<<grid, block, smem, stream>>>(args)  ->  EMU_LAUNCH_EX((kernel<T...>), grid, block, smem, stream, args)
+    extern __shared__ double name[];                      ->  static double name[EMU_DYN_SMEM_DOUBLES];
+The product source is not modified; the output goes to a temporary directory of the test."""
+import os
+import re
+
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))),
+                    "poms_b200", "csrc")
+
+
+def section(path, start_marker, end_marker):
+    text = open(path).read()
+    a = text.index(start_marker)
+    b = text.index(end_marker, a)
+    a = text.rfind("\n", 0, text.rfind("\n", 0, a)) + 1        # include the rule line above the title
+    b = text.rfind("\n", 0, text.rfind("\n", 0, b)) + 1
+    return text[a:b]
+
+
+def to_host(src):
+    src = src.replace("\\\n", " ")                             # join macro continuation lines
+    launch = re.compile(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)<<<([^;]*?)>>>\(([^;()]*)\)")
+    src, n = launch.subn(lambda m: "EMU_LAUNCH_EX((%s), %s, %s)" % (m.group(1), m.group(2), m.group(3)), src)
+    assert "<<<" not in src, "unconverted launch"
+    src = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"static \1 \2[EMU_DYN_SMEM_DOUBLES];", src)
+    return src, n
+
+
+def band_solve_section():
+    src = section(os.path.join(CSRC, "poms_kernels.cu"), "// K4: dgbtrs along one axis",
+                  "// K5: per-axis sparse row gather")
+    return to_host(src)
+
+
+if __name__ == "__main__":
+    s, n = band_solve_section()
+    print(s[:400])
+    print("...", n, "launches converted,", len(s.splitlines()), "lines")

@@ -22,24 +22,44 @@ EMU = os.path.join(ROOT, "tests", "host_emu")
 
 
 @pytest.fixture(scope="module")
-def exes(tmp_path_factory):
+def emu_builds(tmp_path_factory):
+    """The four executables ({transfer, band solve} x {ASan, TSan}), compiled in parallel; -O0: the runs
+    are short and the band-solve harness has 150 template instantiations."""
+    import sys
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("no g++")
+    sys.path.insert(0, EMU)
+    import make_emu_source
     d = tmp_path_factory.mktemp("emu")
+    src, nlaunch = make_emu_source.band_solve_section()
+    assert nlaunch == 5
+    (d / "band_solve_emu.cuh").write_text(src)
     procs = {}
-    for name, flags in (("asan", ["-fsanitize=address", "-fno-omit-frame-pointer"]), ("tsan", ["-fsanitize=thread"])):
-        out = str(d / ("emu_" + name))
-        procs[name] = (out, subprocess.Popen(
-            [gxx, "-std=c++17", "-O1", "-g"] + flags + ["-I" + EMU, os.path.join(EMU, "emu_transfer.cpp"),
-                                                         "-o", out, "-lpthread"],
-            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for prog in ("emu_transfer", "emu_bandsolve"):
+        for name, flags in (("asan", ["-fsanitize=address", "-fno-omit-frame-pointer"]),
+                            ("tsan", ["-fsanitize=thread"])):
+            out = str(d / (prog + "_" + name))
+            procs[prog, name] = (out, subprocess.Popen(
+                [gxx, "-std=c++17", "-O0", "-g"] + flags + ["-I" + EMU, "-I" + str(d),
+                                                             os.path.join(EMU, prog + ".cpp"), "-o", out, "-lpthread"],
+                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     res = {}
-    for name, (out, pr) in procs.items():
+    for key, (out, pr) in procs.items():
         log = pr.communicate()[0]
         assert pr.returncode == 0, log[-3000:]
-        res[name] = out
+        res[key] = out
     return res
+
+
+@pytest.fixture(scope="module")
+def exes(emu_builds):
+    return {san: emu_builds["emu_transfer", san] for san in ("asan", "tsan")}
+
+
+@pytest.fixture(scope="module")
+def bs_exes(emu_builds):
+    return {san: emu_builds["emu_bandsolve", san] for san in ("asan", "tsan")}
 
 
 def _pitch(n):
@@ -145,3 +165,86 @@ def test_transfer_kernels_emulated_on_slab_plan_rows(exes, tmp_path, san, p, N, 
         out = _run(exes[san], tmp_path, op0 + 1, [(s0, c0), P[1], P[2]], ec[lo:hi + 1], xf[fs:fe + 1],
                    (fe - fs + 1, nf[1], nf[2]), (hi - lo + 1, nc[1], nc[2]))
         assert rel(out, xf_ref[fs:fe + 1]) < 1e-14
+
+
+# ------------------------------------------------------------------------------------------------
+# banded line solves (section K4 of poms_kernels.cu): general dgbtrs with pivots, the no-pivot
+# streaming kernels for a strided and for the contiguous axis (cp.async tiles, __syncwarp), the
+# fused epilogue and the chunked substitution -- source rewritten for g++ by host_emu/make_emu_source.py
+# ------------------------------------------------------------------------------------------------
+def _band(rng, n, kl, ku, dominant):
+    from scipy.linalg.lapack import dgbtrf
+    A = np.zeros((n, n))
+    for k in range(-kl, ku + 1):
+        A += np.diag(rng.standard_normal(n - abs(k)), k)
+    if dominant:
+        A += np.diag(np.abs(A).sum(1) + 1.0)
+    ab = np.zeros((2 * kl + ku + 1, n))
+    for j in range(n):
+        for i in range(max(0, j - ku), min(n, j + kl + 1)):
+            ab[kl + ku + i - j, j] = A[i, j]
+    lub, piv, info = dgbtrf(ab, kl, ku)
+    assert info == 0
+    return A, lub, piv
+
+
+def _run_bs(exe, tmp, variant, lub, piv, kl, ku, y, chunk=0, warm=0, scale=1.0, add=None):
+    n_outer, n, n_inner = y.shape
+    hdr = np.array([variant, n, kl, ku, n_outer, n * n_inner, n_inner, n_inner, 0 if piv is None else 1, y.size,
+                    chunk, warm, warm, 0 if add is None else 1, 0, 0], dtype=np.int32)
+    fi, fo = str(tmp / "in.bin"), str(tmp / "out.bin")
+    with open(fi, "wb") as f:
+        hdr.tofile(f)
+        np.array([scale]).tofile(f)
+        np.ascontiguousarray(lub, dtype=np.float64).tofile(f)
+        if piv is not None:
+            np.ascontiguousarray(piv, dtype=np.int32).tofile(f)
+        np.ascontiguousarray(y).tofile(f)
+        if add is not None:
+            np.ascontiguousarray(add).tofile(f)
+    env = dict(os.environ, TSAN_OPTIONS="exitcode=66", ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([exe, fi, fo], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and not r.stderr.strip(), (r.returncode, r.stderr[-4000:])
+    raw = open(fo, "rb").read()
+    assert np.frombuffer(raw[:4], dtype=np.int32)[0] == 0
+    return np.frombuffer(raw[4:], dtype=np.float64).reshape(y.shape)
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("n,kl,ku,dominant", [(37, 1, 1, True), (70, 3, 3, True), (33, 2, 3, False),
+                                              (45, 3, 1, False), (40, 5, 5, True), (9, 1, 1, True)])
+def test_band_solve_kernels_emulated(bs_exes, tmp_path, san, n, kl, ku, dominant):
+    rng = np.random.default_rng(n)
+    A, lub, piv = _band(rng, n, kl, ku, dominant)
+    nopiv = np.array_equal(piv, np.arange(n))
+    assert nopiv == dominant
+    # (n_outer, n, n_inner): strided axis (one thread per line), contiguous axis (warp tiles), ragged
+    for shape in [(3, n, 70), (1, n, 5), (130, n, 1), (7, n, 1)]:
+        y = rng.standard_normal(shape)
+        ref = np.stack([np.linalg.solve(A, y[o]) for o in range(shape[0])])
+        x = _run_bs(bs_exes[san], tmp_path, 0, lub, None if nopiv else piv, kl, ku, y)
+        assert rel(x, ref) < 1e-13
+        if shape[2] == 1 and nopiv:
+            add = rng.standard_normal(shape)
+            x = _run_bs(bs_exes[san], tmp_path, 1, lub, None, kl, ku, y, scale=0.37, add=add)
+            assert rel(x, add + 0.37 * ref) < 1e-13
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("n,kl,ku", [(150, 2, 2), (97, 3, 3)])
+def test_band_chunk_kernels_emulated(bs_exes, tmp_path, san, n, kl, ku):
+    """Chunked substitution against its host model (kron_product.BandLU._emulate_chunked: the same
+    recurrences chunk by chunk, whatever the warm-up length)."""
+    torch = pytest.importorskip("torch")
+    from poms_b200.kron_product import BandLU
+    rng = np.random.default_rng(n)
+    A, lub, piv = _band(rng, n, kl, ku, True)
+    lu = BandLU(lub, kl, ku, piv, torch.device("cpu"))
+    for shape, chunk, warm in [((2, n, 3), 16, 12), ((1, n, 1), 24, 9), ((3, n, 70), 32, 20)]:
+        y = rng.standard_normal(shape)
+        x = _run_bs(bs_exes[san], tmp_path, 2, lub, None, kl, ku, y, chunk=chunk, warm=warm)
+        ref = np.empty(shape)
+        for o in range(shape[0]):
+            for c in range(shape[2]):
+                ref[o, :, c] = lu._emulate_chunked(y[o, :, c], chunk, warm)
+        assert rel(x, ref) < 1e-14
