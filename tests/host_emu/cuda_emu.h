@@ -41,10 +41,26 @@ static long long g_launches;
 #define __launch_bounds__(...)
 #define __host__
 #define __device__
+#define __forceinline__ inline
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
 template <class T>
 static inline T __ldcs(const T* p) { return *p; }
+// warp shuffle: every lane of the warp deposits its value, warp barrier, reads its partner's
+static double emu_shfl_buf[32][32];
+static inline double __shfl_xor_sync(unsigned, double v, int o) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    emu_shfl_buf[w][lane] = v;
+    __syncwarp();
+    const double r = emu_shfl_buf[w][lane ^ o];
+    __syncwarp();
+    return r;
+}
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+template <class T>
+static inline T __ldcg(const T* p) { return *p; }
+#define POMS_HIDDEN
 // round-to-nearest arithmetic that the compiler must not contract into an FMA
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }

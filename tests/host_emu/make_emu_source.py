@@ -34,6 +34,18 @@ def band_solve_section():
     return to_host(src)
 
 
+def generic_mv3_section():
+    """The common device helpers (deterministic grid reduction, shift-form partial sums, MV3) and the
+    generic 3-D Kronecker mat-vec of translation unit 6 (the fallback for tiny or misaligned grids)."""
+    text = open(os.path.join(CSRC, "poms_kernels.cu")).read()
+    a = text.index("// deterministic grid reduction")
+    a = text.rfind("\n", 0, text.rfind("\n", 0, a)) + 1
+    b = text.index("#if POMS_TU == 6")
+    c = text.index("\n", b) + 1
+    d = text.index("#endif  // POMS_TU == 6")
+    return to_host(text[a:b] + text[c:d])
+
+
 if __name__ == "__main__":
     s, n = band_solve_section()
     print(s[:400])

@@ -23,8 +23,8 @@ EMU = os.path.join(ROOT, "tests", "host_emu")
 
 @pytest.fixture(scope="module")
 def emu_builds(tmp_path_factory):
-    """The four executables ({transfer, band solve} x {ASan, TSan}), compiled in parallel; -O0: the runs
-    are short and the band-solve harness has 150 template instantiations."""
+    """The six executables ({transfer, band solve, generic mat-vec} x {ASan, TSan}), compiled in
+    parallel; -O0: the runs are short and the harnesses have up to 150 template instantiations."""
     import sys
     gxx = shutil.which("g++")
     if gxx is None:
@@ -35,13 +35,16 @@ def emu_builds(tmp_path_factory):
     src, nlaunch = make_emu_source.band_solve_section()
     assert nlaunch == 5
     (d / "band_solve_emu.cuh").write_text(src)
+    src, nlaunch = make_emu_source.generic_mv3_section()
+    assert nlaunch == 5
+    (d / "mv3_generic_emu.cuh").write_text(src)
     procs = {}
-    for prog in ("emu_transfer", "emu_bandsolve"):
+    for prog in ("emu_transfer", "emu_bandsolve", "emu_matvec3d"):
         for name, flags in (("asan", ["-fsanitize=address", "-fno-omit-frame-pointer"]),
                             ("tsan", ["-fsanitize=thread"])):
             out = str(d / (prog + "_" + name))
             procs[prog, name] = (out, subprocess.Popen(
-                [gxx, "-std=c++17", "-O0", "-g"] + flags + ["-I" + EMU, "-I" + str(d),
+                [gxx, "-std=c++17", "-O0", "-g"] + flags + ["-I" + EMU, "-I" + str(d), "-I" + os.path.join(ROOT, "include"),
                                                              os.path.join(EMU, prog + ".cpp"), "-o", out, "-lpthread"],
                 stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     res = {}
@@ -60,6 +63,11 @@ def exes(emu_builds):
 @pytest.fixture(scope="module")
 def bs_exes(emu_builds):
     return {san: emu_builds["emu_bandsolve", san] for san in ("asan", "tsan")}
+
+
+@pytest.fixture(scope="module")
+def mv_exes(emu_builds):
+    return {san: emu_builds["emu_matvec3d", san] for san in ("asan", "tsan")}
 
 
 def _pitch(n):
@@ -248,3 +256,94 @@ def test_band_chunk_kernels_emulated(bs_exes, tmp_path, san, n, kl, ku):
             for c in range(shape[2]):
                 ref[o, :, c] = lu._emulate_chunked(y[o, :, c], chunk, warm)
         assert rel(x, ref) < 1e-14
+
+
+# ------------------------------------------------------------------------------------------------
+# generic 3-D Kronecker mat-vec (kron_matvec3d_kernel, translation unit 6: the fallback for tiny or
+# misaligned grids -- every coarse level of a hierarchy runs it) with its five epilogues and the
+# deterministic grid reduction of the fused dot (warp shuffles, ticket counter, last-CTA sum)
+# ------------------------------------------------------------------------------------------------
+def _consts():
+    import re
+    txt = open(os.path.join(ROOT, "include", "poms_b200.h")).read()
+    get = lambda name: int(re.search(r"#define\s+%s\s+(\d+)" % name, txt).group(1))
+    return ({k: get("POMS_EPI_" + k.upper()) for k in ("store", "resid", "jacobi", "dinv", "axpy")},
+            {k: get("POMS_FORM_" + k.upper()) for k in ("single", "sum")})
+
+
+def _run_mv(exe, tmp, p, form, epi, bands, x, b, omega, chunk, has_dot=True):
+    n1, n2, n3 = x.shape
+    ld = n3 + (n3 & 1)
+
+    def pitched(a):
+        t = np.zeros((n1, n2, ld))
+        t[:, :, :n3] = a
+        return t
+
+    hdr = np.zeros(16, dtype=np.int32)
+    hdr[:10] = [p, form, epi, n1, n2, n3, ld, chunk, 0 if b is None else 1, 1 if has_dot else 0]
+    fi, fo = str(tmp / "in.bin"), str(tmp / "out.bin")
+    with open(fi, "wb") as f:
+        hdr.tofile(f)
+        np.array([omega]).tofile(f)
+        for m_, k_ in bands:
+            np.ascontiguousarray(m_, dtype=np.float64).tofile(f)
+            np.ascontiguousarray(k_, dtype=np.float64).tofile(f)
+        pitched(x).tofile(f)
+        if b is not None:
+            pitched(b).tofile(f)
+    env = dict(os.environ, TSAN_OPTIONS="exitcode=66", ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([exe, fi, fo], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0 and not r.stderr.strip(), (r.returncode, r.stderr[-4000:])
+    raw = open(fo, "rb").read()
+    assert np.frombuffer(raw[:4], dtype=np.int32)[0] == 0
+    y = np.frombuffer(raw[12:], dtype=np.float64).reshape(n1, n2, ld)
+    assert not y[:, :, n3:].any()
+    return np.frombuffer(raw[4:12], dtype=np.float64)[0], y[:, :, :n3]
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("p,N,chunk", [(1, (5, 6, 7), 3), (2, (9, 20, 70), 4), (3, (12, 17, 66), 5),
+                                       (4, (10, 18, 30), 20), (5, (8, 9, 10), 4)])
+def test_generic_matvec3d_emulated(mv_exes, tmp_path, san, p, N, chunk):
+    EPI, FORM = _consts()
+    rng = np.random.default_rng(p)
+
+    def randband(n):
+        B = rng.standard_normal((n, 2 * p + 1))
+        i, k = np.indices(B.shape)
+        B[(i + k - p < 0) | (i + k - p >= n)] = 0.0
+        B[:, p] += 4.0
+        return B
+
+    ms, ks = [randband(n) for n in N], [randband(n) for n in N]
+    x, b = rng.standard_normal(N), rng.standard_normal(N)
+    ab, d = po.apply_band, (lambda B: B[:, p])
+
+    def A_sum(v):
+        return (ab(ks[0], ab(ms[1], ab(ms[2], v, 2), 1), 0) + ab(ms[0], ab(ks[1], ab(ms[2], v, 2), 1), 0)
+                + ab(ms[0], ab(ms[1], ab(ks[2], v, 2), 1), 0))
+
+    D_sum = (np.einsum("i,j,k->ijk", d(ks[0]), d(ms[1]), d(ms[2])) + np.einsum("i,j,k->ijk", d(ms[0]), d(ks[1]), d(ms[2]))
+             + np.einsum("i,j,k->ijk", d(ms[0]), d(ms[1]), d(ks[2])))
+    cases = [("sum", A_sum, D_sum),
+             ("single", lambda v: ab(ms[0], ab(ms[1], ab(ms[2], v, 2), 1), 0),
+              np.einsum("i,j,k->ijk", d(ms[0]), d(ms[1]), d(ms[2])))]
+    bands = list(zip(ms, ks))
+    om = 0.7
+    run = lambda form, epi, bb, omega, **kw: _run_mv(mv_exes[san], tmp_path, p, FORM[form], EPI[epi], bands, x, bb,
+                                                     omega, chunk, **kw)
+    for form, A, D in cases:
+        yo = A(x)
+        dr = om * (b - yo) / D
+        dot, y = run(form, "store", None, 1.0)
+        assert rel(y, yo) < 1e-14 and abs(dot - np.vdot(x, yo)) < 1e-13 * np.vdot(np.abs(x), np.abs(yo))
+        dot, y = run(form, "resid", b, 1.0)
+        assert rel(y, b - yo) < 1e-14 and abs(dot - np.vdot(b - yo, b - yo)) < 1e-13 * dot
+        dot, y = run(form, "jacobi", b, om)
+        assert rel(y, x + dr) < 1e-14 and abs(dot - np.vdot(dr, dr)) < 1e-13 * dot
+        if san == "asan":                     # (the remaining epilogues share every barrier with the ones above)
+            assert rel(run(form, "dinv", b, om, has_dot=False)[1], dr) < 1e-14
+            dot, y = run(form, "axpy", b, om)
+            assert rel(y, b + om * yo) < 1e-14 and abs(dot - np.vdot(om * yo, om * yo)) < 1e-13 * dot
+            assert rel(run(form, "axpy", None, om)[1], om * yo) < 1e-14
