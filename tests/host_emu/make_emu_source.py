@@ -46,6 +46,27 @@ def generic_mv3_section():
     return to_host(text[a:b] + text[c:d])
 
 
+def tu0_middle_section():
+    """Translation unit 0 between the 2-D mat-vec and the band solves: round-1 2-D Kronecker mat-vec
+    (tiny / misaligned grids) with its entry point, full 2-D stencil mat-vec, the CG vector algebra
+    (cg_update, p_update, dot, axpby, ...), jacobi_first -- preceded by the common device helpers and
+    the axis-1 chunk rule they use.  The TMA fast path of the 2-D entry is stubbed out by the harness
+    (try_matvec2d_tma returns "not applicable")."""
+    text = open(os.path.join(CSRC, "poms_kernels.cu")).read()
+    a = text.index("// deterministic grid reduction")
+    a = text.rfind("\n", 0, text.rfind("\n", 0, a)) + 1
+    b = text.index("#if POMS_TU == 6")
+    c = text.index("static int g_chunk_override = 0;")
+    d = text.index("#endif", c)
+    e = text.index("// K1: Kronecker banded mat-vec, 2-D.")
+    e = text.rfind("\n", 0, text.rfind("\n", 0, e)) + 1
+    f = text.index("// K4: dgbtrs along one axis")
+    f = text.rfind("\n", 0, text.rfind("\n", 0, f)) + 1
+    stub = ("static int try_matvec2d_tma(const MV2&, int, int, int, const double*, const int*, cudaStream_t) "
+            "{ return 1; }\n")
+    return to_host(text[a:b] + text[c:d] + stub + text[e:f])
+
+
 if __name__ == "__main__":
     s, n = band_solve_section()
     print(s[:400])

@@ -23,8 +23,8 @@ EMU = os.path.join(ROOT, "tests", "host_emu")
 
 @pytest.fixture(scope="module")
 def emu_builds(tmp_path_factory):
-    """The six executables ({transfer, band solve, generic mat-vec} x {ASan, TSan}), compiled in
-    parallel; -O0: the runs are short and the harnesses have up to 150 template instantiations."""
+    """The eight executables ({transfer, band solve, generic 3-D mat-vec, 2-D mat-vec + vector
+    algebra} x {ASan, TSan}), compiled in parallel; -O0: the runs are short and the harnesses have up to 150 template instantiations."""
     import sys
     gxx = shutil.which("g++")
     if gxx is None:
@@ -38,8 +38,11 @@ def emu_builds(tmp_path_factory):
     src, nlaunch = make_emu_source.generic_mv3_section()
     assert nlaunch == 5
     (d / "mv3_generic_emu.cuh").write_text(src)
+    src, nlaunch = make_emu_source.tu0_middle_section()
+    assert nlaunch == 18
+    (d / "tu0_middle_emu.cuh").write_text(src)
     procs = {}
-    for prog in ("emu_transfer", "emu_bandsolve", "emu_matvec3d"):
+    for prog in ("emu_transfer", "emu_bandsolve", "emu_matvec3d", "emu_tu0"):
         for name, flags in (("asan", ["-fsanitize=address", "-fno-omit-frame-pointer"]),
                             ("tsan", ["-fsanitize=thread"])):
             out = str(d / (prog + "_" + name))
@@ -68,6 +71,11 @@ def bs_exes(emu_builds):
 @pytest.fixture(scope="module")
 def mv_exes(emu_builds):
     return {san: emu_builds["emu_matvec3d", san] for san in ("asan", "tsan")}
+
+
+@pytest.fixture(scope="module")
+def tu0_exes(emu_builds):
+    return {san: emu_builds["emu_tu0", san] for san in ("asan", "tsan")}
 
 
 def _pitch(n):
@@ -347,3 +355,102 @@ def test_generic_matvec3d_emulated(mv_exes, tmp_path, san, p, N, chunk):
             dot, y = run(form, "axpy", b, om)
             assert rel(y, b + om * yo) < 1e-14 and abs(dot - np.vdot(om * yo, om * yo)) < 1e-13 * dot
             assert rel(run(form, "axpy", None, om)[1], om * yo) < 1e-14
+
+
+# ------------------------------------------------------------------------------------------------
+# round-1 2-D Kronecker mat-vec through poms_kron_matvec_2d (tiny / misaligned grids: C1; the TMA fast
+# path is stubbed out), poms_jacobi_first_2d, and the vector algebra of the CG drivers
+# ------------------------------------------------------------------------------------------------
+def _call_tu0(exe, tmp, hdr_vals, scal, arrays, out_sizes):
+    hdr = np.zeros(16, dtype=np.int32)
+    hdr[:len(hdr_vals)] = hdr_vals
+    sc = np.zeros(4)
+    sc[:len(scal)] = scal
+    fi, fo = str(tmp / "in.bin"), str(tmp / "out.bin")
+    with open(fi, "wb") as f:
+        hdr.tofile(f)
+        sc.tofile(f)
+        for a in arrays:
+            np.ascontiguousarray(a, dtype=np.float64).tofile(f)
+    env = dict(os.environ, TSAN_OPTIONS="exitcode=66", ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([exe, fi, fo], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0 and not r.stderr.strip(), (r.returncode, r.stderr[-4000:])
+    raw = open(fo, "rb").read()
+    assert np.frombuffer(raw[:4], dtype=np.int32)[0] == 0
+    outs, off = [], 12
+    for n in out_sizes:
+        outs.append(np.frombuffer(raw[off:off + 8 * n], dtype=np.float64))
+        off += 8 * n
+    return np.frombuffer(raw[4:12], dtype=np.float64)[0], outs
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("p,N", [(1, (16, 16)), (2, (10, 13)), (3, (64, 64)), (5, (40, 300)), (4, (9, 9)),
+                                 (3, (7, 515)), (2, (300, 5))])
+def test_matvec2d_round1_emulated(tu0_exes, tmp_path, san, p, N):
+    EPI, FORM = _consts()
+    rng = np.random.default_rng(p + N[1])
+
+    def randband(n):
+        B = rng.standard_normal((n, 2 * p + 1))
+        i, k = np.indices(B.shape)
+        B[(i + k - p < 0) | (i + k - p >= n)] = 0.0
+        B[:, p] += 4.0
+        return B
+
+    ms, ks = [randband(n) for n in N], [randband(n) for n in N]
+    x, b = rng.standard_normal(N), rng.standard_normal(N)
+    n1, n2 = N
+    ld = n2 + (n2 & 1)
+    pit = lambda a: np.pad(a, ((0, 0), (0, ld - n2)))
+
+    def mv2(form, epi, bb, omega, has_dot=True, op=0):
+        arrays = [ms[0], ks[0], ms[1], ks[1], pit(x)] + ([pit(bb)] if bb is not None else [])
+        dot, (y,) = _call_tu0(tu0_exes[san], tmp_path, [op, n1, n2, ld, p, FORM[form], EPI[epi], 0 if bb is None else 1,
+                                                         1 if has_dot else 0, 0], [omega], arrays, [n1 * ld])
+        y = y.reshape(n1, ld)
+        assert not y[:, n2:].any()
+        return dot, y[:, :n2]
+
+    ab, d = po.apply_band, (lambda B: B[:, p])
+    om = 0.7
+    for form, A, D in (("sum", lambda v: ab(ks[0], ab(ms[1], v, 1), 0) + ab(ms[0], ab(ks[1], v, 1), 0),
+                        np.outer(d(ks[0]), d(ms[1])) + np.outer(d(ms[0]), d(ks[1]))),
+                       ("single", lambda v: ab(ms[0], ab(ms[1], v, 1), 0), np.outer(d(ms[0]), d(ms[1])))):
+        yo = A(x)
+        dr = om * (b - yo) / D
+        dot, y = mv2(form, "store", None, 1.0)
+        assert rel(y, yo) < 1e-14 and abs(dot - np.vdot(x, yo)) < 1e-13 * np.vdot(np.abs(x), np.abs(yo))
+        dot, y = mv2(form, "resid", b, 1.0)
+        assert rel(y, b - yo) < 1e-14 and abs(dot - np.vdot(b - yo, b - yo)) < 1e-13 * dot
+        dot, y = mv2(form, "jacobi", b, om)
+        assert rel(y, x + dr) < 1e-14 and abs(dot - np.vdot(dr, dr)) < 1e-13 * dot
+        if san == "asan":
+            assert rel(mv2(form, "dinv", b, om, has_dot=False)[1], dr) < 1e-14
+            assert rel(mv2(form, "axpy", b, om)[1], b + om * yo) < 1e-14
+            dot, y = mv2(form, "store", b, om, op=5)               # poms_jacobi_first_2d
+            assert rel(y, om * b / D) < 1e-14 and abs(dot - np.vdot(y, y)) < 1e-13 * dot
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("n", [1, 31, 1000, 100003])
+def test_cg_vector_algebra_emulated(tu0_exes, tmp_path, san, n):
+    """poms_cg_update, poms_p_update, poms_dot, poms_axpby, poms_cheb_update
+    (/root/reference/sources/solvers.py:104-124) with the deterministic grid reduction."""
+    rng = np.random.default_rng(n)
+    a = [rng.standard_normal(n) for _ in range(4)]
+    num, den = 1.7, -0.9
+    al = num / den
+    exe = tu0_exes[san]
+    dot, (x, r) = _call_tu0(exe, tmp_path, [1, 0, 0, 0, 0, 0, 0, 0, 1, n], [0, num, den, 0], a, [n, n])
+    rr = a[1] - al * a[3]
+    assert rel(x, a[0] + al * a[2]) < 1e-15 and rel(r, rr) < 1e-15 and abs(dot - np.vdot(rr, rr)) < 1e-13 * dot
+    dot, (pp,) = _call_tu0(exe, tmp_path, [2, 0, 0, 0, 0, 0, 0, 0, 0, n], [0, num, den, 0], a, [n])
+    assert rel(pp, a[1] + al * a[0]) < 1e-15
+    dot, _ = _call_tu0(exe, tmp_path, [3, 0, 0, 0, 0, 0, 0, 0, 1, n], [], a, [])
+    assert abs(dot - np.vdot(a[0], a[1])) < 1e-13 * np.vdot(np.abs(a[0]), np.abs(a[1]))
+    dot, (z,) = _call_tu0(exe, tmp_path, [4, 0, 0, 0, 0, 0, 0, 0, 0, n], [0.3, -1.1], a, [n])
+    assert rel(z, 0.3 * a[1] - 1.1 * a[2]) < 1e-15
+    dot, (x, dd) = _call_tu0(exe, tmp_path, [6, 0, 0, 0, 0, 0, 0, 0, 0, n], [0.25, 0, 0, 1.5], a, [n, n])
+    dn = 0.25 * a[1] + 1.5 * a[2]
+    assert rel(dd, dn) < 1e-15 and rel(x, a[0] + dn) < 1e-15
