@@ -46,6 +46,10 @@ template <class T>
 static inline T __ldg(const T* p) { return *p; }
 template <class T>
 static inline T __ldcs(const T* p) { return *p; }
+struct alignas(16) double2 {
+    double x, y;
+};
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 // warp shuffle: every lane of the warp deposits its value, warp barrier, reads its partner's
 static double emu_shfl_buf[32][32];
 static inline double __shfl_xor_sync(unsigned, double v, int o) {

@@ -67,6 +67,65 @@ def tu0_middle_section():
     return to_host(text[a:b] + text[c:d] + stub + text[e:f])
 
 
+def _strip_functions(src, names):
+    """Remove the definitions of small `__device__ __forceinline__ void NAME(...) { ... }` wrappers
+    (inline PTX): the emulation header provides their host versions."""
+    for name in names:
+        src, n = re.subn(r"__device__ __forceinline__ void %s\(.*?\n}\n" % name, "", src, flags=re.S)
+        assert n == 1, (name, n)
+    return src
+
+
+def tma_mv3_section(degrees=(2, 3, 4)):
+    """The hot path: TMA-staged 3-D Kronecker mat-vec (poms_matvec3d_tma.cuh + poms_matvec3d_v3.cuh)
+    behind poms_kron_matvec_3d_dotv, with the generic kernel as its fallback.  The device section that
+    build.py compiles once per degree (-DPOMS_TU=p) is instantiated textually per degree inside a
+    namespace; the inline-PTX wrappers (mbarrier, cp.async.bulk.tensor) are removed, emu_tma.h provides
+    them; degrees that are not built answer "bad argument"."""
+    text = open(os.path.join(CSRC, "poms_kernels.cu")).read()
+    tma = open(os.path.join(CSRC, "poms_matvec3d_tma.cuh")).read()
+    v3 = open(os.path.join(CSRC, "poms_matvec3d_v3.cuh")).read().replace("#pragma once", "")
+    # common helpers + generic kernel (fallback) + chunk rule
+    a = text.index("// deterministic grid reduction")
+    a = text.rfind("\n", 0, text.rfind("\n", 0, a)) + 1
+    b = text.index("#if POMS_TU == 6")
+    c = text.index("\n", b) + 1
+    d = text.index("#endif  // POMS_TU == 6")
+    ck = text.index("static int g_chunk_override = 0;")
+    ckd = text.index("#endif", ck)
+    out = text[a:b] + text[c:d] + text[ck:ckd]
+    # poms_matvec3d_tma.cuh: declarations before the per-degree section
+    h0 = tma.index("struct MV3T {")
+    h1 = tma.index("#if POMS_TU >= 1 && POMS_TU <= 5")
+    out += _strip_functions(tma[h0:h1], ["mbar_init", "mbar_expect_tx", "mbar_wait", "tma_load_3d"])
+    d0 = tma.index("\n", h1) + 1
+    d1 = tma.index("#endif  // POMS_TU in 1..5")
+    dev = tma[d0:d1].replace('#include "poms_matvec3d_v3.cuh"', _strip_functions(v3, ["mbar_arrive"]))
+    dev = re.sub(r'[ \t]*asm volatile\("fence[^\n]*\n', "", dev)
+    assert "asm volatile" not in dev
+    dev = re.sub(r"extern __shared__ __align__\(1024\) unsigned char smem_raw\[\];",
+                 "alignas(1024) static unsigned char smem_raw[EMU_DYN_SMEM_DOUBLES * 8];", dev)
+    sig = ("(const CUtensorMap* tm3, const MV3T& g, int form, int epi, int variant, int ntiles, dim3 grid, "
+           "cudaStream_t st)")
+    for P in range(1, 6):
+        if P in degrees:
+            out += "namespace emu_tu%d {\n#undef POMS_MV3_BLOCKS\n%s\n}\n" % (P, re.sub(r"\bPOMS_TU\b", str(P), dev))
+            out += ("int poms_mv3_tma_launch_p%d%s { return emu_tu%d::poms_mv3_tma_launch_p%d(tm3, g, form, epi, "
+                    "variant, ntiles, grid, st); }\n" % (P, sig, P, P))
+        else:
+            out += 'int poms_mv3_tma_launch_p%d%s { return bad_arg(11, "degree not built in the emulation"); }\n' % (P, sig)
+    # host side of the TMA path (tensor-map cache, dispatch) and the C entry points
+    t0 = tma.index("#if POMS_TU == 0")
+    t0 = tma.index("\n", t0) + 1
+    t1 = tma.index("#endif  // POMS_TU == 0")
+    out += tma[t0:t1]
+    e0 = text.index('extern "C" int poms_kron_matvec_3d_ex(')
+    e1 = text.index("// K1: Kronecker banded mat-vec, 2-D.")
+    e1 = text.rfind("\n", 0, text.rfind("\n", 0, e1)) + 1
+    out += text[e0:e1]
+    return to_host(out)
+
+
 if __name__ == "__main__":
     s, n = band_solve_section()
     print(s[:400])

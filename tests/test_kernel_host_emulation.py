@@ -23,8 +23,8 @@ EMU = os.path.join(ROOT, "tests", "host_emu")
 
 @pytest.fixture(scope="module")
 def emu_builds(tmp_path_factory):
-    """The eight executables ({transfer, band solve, generic 3-D mat-vec, 2-D mat-vec + vector
-    algebra} x {ASan, TSan}), compiled in parallel; -O0: the runs are short and the harnesses have up to 150 template instantiations."""
+    """The ten executables ({TMA 3-D mat-vec, transfer, band solve, generic 3-D mat-vec, 2-D mat-vec +
+    vector algebra} x {ASan, TSan}), compiled in parallel; -O0: the runs are short and the harnesses have up to 150 template instantiations."""
     import sys
     gxx = shutil.which("g++")
     if gxx is None:
@@ -41,13 +41,19 @@ def emu_builds(tmp_path_factory):
     src, nlaunch = make_emu_source.tu0_middle_section()
     assert nlaunch == 18
     (d / "tu0_middle_emu.cuh").write_text(src)
+    src, nlaunch = make_emu_source.tma_mv3_section((2, 3, 4))
+    (d / "mv3_tma_emu.cuh").write_text(src)
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     procs = {}
-    for prog in ("emu_transfer", "emu_bandsolve", "emu_matvec3d", "emu_tu0"):
+    for prog in ("emu_matvec3d_tma", "emu_transfer", "emu_bandsolve", "emu_matvec3d", "emu_tu0"):
+        if prog == "emu_matvec3d_tma" and not os.path.exists(os.path.join(cuda_inc, "cuda.h")):
+            continue
         for name, flags in (("asan", ["-fsanitize=address", "-fno-omit-frame-pointer"]),
                             ("tsan", ["-fsanitize=thread"])):
             out = str(d / (prog + "_" + name))
             procs[prog, name] = (out, subprocess.Popen(
                 [gxx, "-std=c++17", "-O0", "-g"] + flags + ["-I" + EMU, "-I" + str(d), "-I" + os.path.join(ROOT, "include"),
+                                                             "-I" + cuda_inc,
                                                              os.path.join(EMU, prog + ".cpp"), "-o", out, "-lpthread"],
                 stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     res = {}
@@ -71,6 +77,13 @@ def bs_exes(emu_builds):
 @pytest.fixture(scope="module")
 def mv_exes(emu_builds):
     return {san: emu_builds["emu_matvec3d", san] for san in ("asan", "tsan")}
+
+
+@pytest.fixture(scope="module")
+def tma_exes(emu_builds):
+    if ("emu_matvec3d_tma", "asan") not in emu_builds:
+        pytest.skip("no <cuda.h> (the emulation uses the real CUtensorMap type)")
+    return {san: emu_builds["emu_matvec3d_tma", san] for san in ("asan", "tsan")}
 
 
 @pytest.fixture(scope="module")
@@ -386,7 +399,7 @@ def _call_tu0(exe, tmp, hdr_vals, scal, arrays, out_sizes):
 
 @pytest.mark.parametrize("san", ["asan", "tsan"])
 @pytest.mark.parametrize("p,N", [(1, (16, 16)), (2, (10, 13)), (3, (64, 64)), (5, (40, 300)), (4, (9, 9)),
-                                 (3, (7, 515)), (2, (300, 5))])
+                                 (3, (7, 515)), (2, (120, 5))])
 def test_matvec2d_round1_emulated(tu0_exes, tmp_path, san, p, N):
     EPI, FORM = _consts()
     rng = np.random.default_rng(p + N[1])
@@ -454,3 +467,108 @@ def test_cg_vector_algebra_emulated(tu0_exes, tmp_path, san, n):
     dot, (x, dd) = _call_tu0(exe, tmp_path, [6, 0, 0, 0, 0, 0, 0, 0, 0, n], [0.25, 0, 0, 1.5], a, [n, n])
     dn = 0.25 * a[1] + 1.5 * a[2]
     assert rel(dd, dn) < 1e-15 and rel(x, a[0] + dn) < 1e-15
+
+
+# ------------------------------------------------------------------------------------------------
+# THE HOT PATH: TMA-staged 3-D Kronecker mat-vec (kron_matvec3d_v3_kernel, and the round-1
+# kron_matvec3d_tma_kernel kept as variant 0) through poms_kron_matvec_3d_dotv.  host_emu/emu_tma.h
+# stands in for the tensor map, cp.async.bulk.tensor (immediate copy, zero fill outside the tensor) and
+# the mbarrier (arrival / byte counts and phase under a mutex); tensor-map creation, Toeplitz tables,
+# variant selection and chunking are the product's own host code.
+# ------------------------------------------------------------------------------------------------
+def _toeplitz_tables(ms, ks, p):
+    """stencil.KronSumMatrix._toeplitz: interior rows bit-identical to the middle row, per axis."""
+    W = 2 * p + 1
+    coef, rng = np.zeros((3, 2, W)), np.zeros(6, dtype=np.int32)
+    for a in range(3):
+        m, k = ms[a], ks[a]
+        n = m.shape[0]
+        mid = n // 2
+        same = np.all(m == m[mid], axis=1) & np.all(k == k[mid], axis=1)
+        lo, hi = mid, mid + 1
+        while lo > 0 and same[lo - 1]:
+            lo -= 1
+        while hi < n and same[hi]:
+            hi += 1
+        coef[a, 0], coef[a, 1] = m[mid], k[mid]
+        rng[2 * a], rng[2 * a + 1] = lo, hi
+    return coef, rng
+
+
+def _run_tma(exe, tmp, p, form, epi, ms, ks, x, b, omega, variant, toep, has_dot=True):
+    n1, n2, n3 = x.shape
+    ld = n3 + (n3 & 1)
+    pit = lambda a: np.pad(a, ((0, 0), (0, 0), (0, ld - n3)))
+    hdr = np.zeros(16, dtype=np.int32)
+    hdr[:13] = [p, form, epi, n1, n2, n3, ld, variant, 0 if b is None else 1, 1 if has_dot else 0,
+                0 if toep is None else 1, 0, 0]
+    fi, fo = str(tmp / "in.bin"), str(tmp / "out.bin")
+    with open(fi, "wb") as f:
+        hdr.tofile(f)
+        np.array([omega]).tofile(f)
+        for a in range(3):
+            np.ascontiguousarray(ms[a]).tofile(f)
+            np.ascontiguousarray(ks[a]).tofile(f)
+        if toep is not None:
+            np.ascontiguousarray(toep[0]).tofile(f)
+            np.ascontiguousarray(toep[1], dtype=np.int32).tofile(f)
+        pit(x).tofile(f)
+        if b is not None:
+            pit(b).tofile(f)
+    env = dict(os.environ, TSAN_OPTIONS="exitcode=66", ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([exe, fi, fo], capture_output=True, text=True, env=env, timeout=1200)
+    assert r.returncode == 0 and not r.stderr.strip(), (r.returncode, r.stderr[-4000:])
+    raw = open(fo, "rb").read()
+    assert np.frombuffer(raw[:4], dtype=np.int32)[0] == 0
+    dot, ntma = np.frombuffer(raw[8:24], dtype=np.float64)
+    assert ntma > 0, "the TMA path was not taken"
+    y = np.frombuffer(raw[24:], dtype=np.float64).reshape(n1, n2, ld)
+    assert not y[:, :, n3:].any()
+    return dot, y[:, :, :n3]
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("p,N,variant", [(3, (20, 20, 70), 1), (3, (20, 20, 70), 0), (3, (30, 50, 200), 1),
+                                         (3, (12, 40, 140), 0), (2, (14, 30, 100), 1), (4, (12, 28, 90), 1)])
+def test_tma_matvec3d_emulated(tma_exes, tmp_path, san, p, N, variant):
+    """Operator of the bench (p = 3, Kronecker sum of the assembled mass / stiffness bands: Toeplitz
+    interior rows from the constant bank, boundary rows from memory, ragged tiles; (30, 50, 200) also
+    has interior tiles on the check-free fast path) and single Kronecker products of degree 2 and 4 (the
+    shapes of the two smoother factors), every epilogue the V-cycle uses."""
+    if san == "tsan" and N == (30, 50, 200):
+        pytest.skip("largest case under the address sanitizer only")
+    EPI, FORM = _consts()
+    nf = [n + p for n in N]
+    MK = [bs.assemble_1d_bands(p, bs.make_open_knots(p, n)) for n in nf]
+    ms, ks = [m for m, k in MK], [k for m, k in MK]
+    ks[2] = ks[2] + ms[2]
+    toep = _toeplitz_tables(ms, ks, p)
+    assert all(toep[1][2 * a + 1] - toep[1][2 * a] >= nf[a] - 4 * p for a in range(3))
+    rng = np.random.default_rng(p)
+    x, b = rng.standard_normal(nf), rng.standard_normal(nf)
+    ab, d = po.apply_band, (lambda B: B[:, p])
+    A_sum = lambda v: (ab(ks[0], ab(ms[1], ab(ms[2], v, 2), 1), 0) + ab(ms[0], ab(ks[1], ab(ms[2], v, 2), 1), 0)
+                       + ab(ms[0], ab(ms[1], ab(ks[2], v, 2), 1), 0))
+    D_sum = (np.einsum("i,j,k->ijk", d(ks[0]), d(ms[1]), d(ms[2])) + np.einsum("i,j,k->ijk", d(ms[0]), d(ks[1]), d(ms[2]))
+             + np.einsum("i,j,k->ijk", d(ms[0]), d(ms[1]), d(ks[2])))
+    cases = [("single", lambda v: ab(ms[0], ab(ms[1], ab(ms[2], v, 2), 1), 0),
+              np.einsum("i,j,k->ijk", d(ms[0]), d(ms[1]), d(ms[2])))]
+    if p == 3:
+        cases.insert(0, ("sum", A_sum, D_sum))
+    om = 0.7
+    run = lambda form, epi, bb, omega, **kw: _run_tma(tma_exes[san], tmp_path, p, FORM[form], EPI[epi], ms, ks, x, bb,
+                                                      omega, variant, toep, **kw)
+    for form, A, D in cases:
+        yo = A(x)
+        dr = om * (b - yo) / D
+        tol = 1e-14
+        dot, y = run(form, "store", None, 1.0)
+        assert rel(y, yo) < tol and abs(dot - np.vdot(x, yo)) < 1e-13 * np.vdot(np.abs(x), np.abs(yo))
+        dot, y = run(form, "resid", b, 1.0)
+        assert rel(y, b - yo) < tol and abs(dot - np.vdot(b - yo, b - yo)) < 1e-13 * dot
+        if san == "tsan" or max(N) >= 200:
+            continue                          # (the other epilogues share every barrier with these two)
+        assert rel(run(form, "axpy", b, om)[1], b + om * yo) < tol
+        assert rel(run(form, "axpy", None, om)[1], om * yo) < tol
+        dot, y = run(form, "jacobi", b, om)
+        assert rel(y, x + dr) < tol and abs(dot - np.vdot(dr, dr)) < 1e-13 * dot
