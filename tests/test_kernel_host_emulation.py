@@ -19,6 +19,20 @@ from oracle import poms_oracle as po
 from poms_b200 import bsplines as bs
 
 EMU = os.path.join(ROOT, "tests", "host_emu")
+# Default run (the driver's CPU suite): a CORE set -- one or two cases per kernel family under the address
+# sanitizer, the thread sanitizer on the two newest families (TMA mat-vec, one-pass transfers).
+# POMS_EMU_FULL=1 runs every case under both sanitizers (profiles/r02_host_emulation_kernels.txt is such a
+# run; it takes 3 to 10 minutes depending on the machine: 256 OS threads per emulated block).
+FULL = os.environ.get("POMS_EMU_FULL") == "1"
+TSAN_PROGS = ("emu_matvec3d_tma", "emu_transfer")
+
+
+def _core(san, core_asan, core_tsan=False):
+    """Skip unless the case belongs to the core set (or the full run was requested)."""
+    if FULL:
+        return
+    if (san == "asan" and not core_asan) or (san == "tsan" and not core_tsan):
+        pytest.skip("not in the core set (POMS_EMU_FULL=1 runs every case under both sanitizers)")
 
 
 @pytest.fixture(scope="module")
@@ -50,6 +64,8 @@ def emu_builds(tmp_path_factory):
             continue
         for name, flags in (("asan", ["-fsanitize=address", "-fno-omit-frame-pointer"]),
                             ("tsan", ["-fsanitize=thread"])):
+            if name == "tsan" and not FULL and prog not in TSAN_PROGS:
+                continue
             out = str(d / (prog + "_" + name))
             procs[prog, name] = (out, subprocess.Popen(
                 [gxx, "-std=c++17", "-O0", "-g"] + flags + ["-I" + EMU, "-I" + str(d), "-I" + os.path.join(ROOT, "include"),
@@ -66,29 +82,29 @@ def emu_builds(tmp_path_factory):
 
 @pytest.fixture(scope="module")
 def exes(emu_builds):
-    return {san: emu_builds["emu_transfer", san] for san in ("asan", "tsan")}
+    return {san: emu_builds.get(("emu_transfer", san)) for san in ("asan", "tsan")}
 
 
 @pytest.fixture(scope="module")
 def bs_exes(emu_builds):
-    return {san: emu_builds["emu_bandsolve", san] for san in ("asan", "tsan")}
+    return {san: emu_builds.get(("emu_bandsolve", san)) for san in ("asan", "tsan")}
 
 
 @pytest.fixture(scope="module")
 def mv_exes(emu_builds):
-    return {san: emu_builds["emu_matvec3d", san] for san in ("asan", "tsan")}
+    return {san: emu_builds.get(("emu_matvec3d", san)) for san in ("asan", "tsan")}
 
 
 @pytest.fixture(scope="module")
 def tma_exes(emu_builds):
     if ("emu_matvec3d_tma", "asan") not in emu_builds:
         pytest.skip("no <cuda.h> (the emulation uses the real CUtensorMap type)")
-    return {san: emu_builds["emu_matvec3d_tma", san] for san in ("asan", "tsan")}
+    return {san: emu_builds.get(("emu_matvec3d_tma", san)) for san in ("asan", "tsan")}
 
 
 @pytest.fixture(scope="module")
 def tu0_exes(emu_builds):
-    return {san: emu_builds["emu_tu0", san] for san in ("asan", "tsan")}
+    return {san: emu_builds.get(("emu_tu0", san)) for san in ("asan", "tsan")}
 
 
 def _pitch(n):
@@ -157,8 +173,7 @@ GEN = {"round2": 0, "round1": 2}
 @pytest.mark.parametrize("san", ["asan", "tsan"])
 @pytest.mark.parametrize("p,N", CASES)
 def test_transfer_kernels_emulated(exes, tmp_path, san, p, N, gen):
-    if san == "tsan" and max(N) > 100 and p != 3:
-        pytest.skip("the thread sanitizer runs one long-axis case per kernel family")
+    _core(san, p == 3 and N == (20, 36, 140), p == 3 and N == (20, 36, 140) and gen == "round2")
     op0 = GEN[gen]
     nf, nc, P, R, P1s = _tables(p, N)
     rng = np.random.default_rng(1)
@@ -175,6 +190,7 @@ def test_transfer_kernels_emulated_on_slab_plan_rows(exes, tmp_path, san, p, N, 
     of the inner ranks start BEFORE the block (leading zero coefficients).  The round-1 prolongation
     kernel read those planes out of bounds until this test ran it under AddressSanitizer."""
     from poms_b200.dist import slab_transfer_plan
+    _core(san, size == 2)
     op0 = GEN[gen]
     nf, nc, P, R, P1s = _tables(p, N)
     rng = np.random.default_rng(5)
@@ -243,6 +259,7 @@ def _run_bs(exe, tmp, variant, lub, piv, kl, ku, y, chunk=0, warm=0, scale=1.0, 
 @pytest.mark.parametrize("n,kl,ku,dominant", [(37, 1, 1, True), (70, 3, 3, True), (33, 2, 3, False),
                                               (45, 3, 1, False), (40, 5, 5, True), (9, 1, 1, True)])
 def test_band_solve_kernels_emulated(bs_exes, tmp_path, san, n, kl, ku, dominant):
+    _core(san, (n, kl) in ((70, 3), (33, 2)))
     rng = np.random.default_rng(n)
     A, lub, piv = _band(rng, n, kl, ku, dominant)
     nopiv = np.array_equal(piv, np.arange(n))
@@ -266,6 +283,7 @@ def test_band_chunk_kernels_emulated(bs_exes, tmp_path, san, n, kl, ku):
     recurrences chunk by chunk, whatever the warm-up length)."""
     torch = pytest.importorskip("torch")
     from poms_b200.kron_product import BandLU
+    _core(san, n == 97)
     rng = np.random.default_rng(n)
     A, lub, piv = _band(rng, n, kl, ku, True)
     lu = BandLU(lub, kl, ku, piv, torch.device("cpu"))
@@ -327,6 +345,7 @@ def _run_mv(exe, tmp, p, form, epi, bands, x, b, omega, chunk, has_dot=True):
 @pytest.mark.parametrize("p,N,chunk", [(1, (5, 6, 7), 3), (2, (9, 20, 70), 4), (3, (12, 17, 66), 5),
                                        (4, (10, 18, 30), 20), (5, (8, 9, 10), 4)])
 def test_generic_matvec3d_emulated(mv_exes, tmp_path, san, p, N, chunk):
+    _core(san, p == 3)
     EPI, FORM = _consts()
     rng = np.random.default_rng(p)
 
@@ -354,7 +373,7 @@ def test_generic_matvec3d_emulated(mv_exes, tmp_path, san, p, N, chunk):
     om = 0.7
     run = lambda form, epi, bb, omega, **kw: _run_mv(mv_exes[san], tmp_path, p, FORM[form], EPI[epi], bands, x, bb,
                                                      omega, chunk, **kw)
-    for form, A, D in cases:
+    for form, A, D in (cases if FULL else cases[:1]):
         yo = A(x)
         dr = om * (b - yo) / D
         dot, y = run(form, "store", None, 1.0)
@@ -363,7 +382,7 @@ def test_generic_matvec3d_emulated(mv_exes, tmp_path, san, p, N, chunk):
         assert rel(y, b - yo) < 1e-14 and abs(dot - np.vdot(b - yo, b - yo)) < 1e-13 * dot
         dot, y = run(form, "jacobi", b, om)
         assert rel(y, x + dr) < 1e-14 and abs(dot - np.vdot(dr, dr)) < 1e-13 * dot
-        if san == "asan":                     # (the remaining epilogues share every barrier with the ones above)
+        if san == "asan" and FULL:            # (the remaining epilogues share every barrier with the ones above)
             assert rel(run(form, "dinv", b, om, has_dot=False)[1], dr) < 1e-14
             dot, y = run(form, "axpy", b, om)
             assert rel(y, b + om * yo) < 1e-14 and abs(dot - np.vdot(om * yo, om * yo)) < 1e-13 * dot
@@ -401,6 +420,7 @@ def _call_tu0(exe, tmp, hdr_vals, scal, arrays, out_sizes):
 @pytest.mark.parametrize("p,N", [(1, (16, 16)), (2, (10, 13)), (3, (64, 64)), (5, (40, 300)), (4, (9, 9)),
                                  (3, (7, 515)), (2, (120, 5))])
 def test_matvec2d_round1_emulated(tu0_exes, tmp_path, san, p, N):
+    _core(san, N == (64, 64))
     EPI, FORM = _consts()
     rng = np.random.default_rng(p + N[1])
 
@@ -450,6 +470,7 @@ def test_matvec2d_round1_emulated(tu0_exes, tmp_path, san, p, N):
 def test_cg_vector_algebra_emulated(tu0_exes, tmp_path, san, n):
     """poms_cg_update, poms_p_update, poms_dot, poms_axpby, poms_cheb_update
     (/root/reference/sources/solvers.py:104-124) with the deterministic grid reduction."""
+    _core(san, n == 1000)
     rng = np.random.default_rng(n)
     a = [rng.standard_normal(n) for _ in range(4)]
     num, den = 1.7, -0.9
@@ -537,6 +558,7 @@ def test_tma_matvec3d_emulated(tma_exes, tmp_path, san, p, N, variant):
     shapes of the two smoother factors), every epilogue the V-cycle uses."""
     if san == "tsan" and N == (30, 50, 200):
         pytest.skip("largest case under the address sanitizer only")
+    _core(san, variant == 1 and N in ((20, 20, 70), (14, 30, 100), (12, 28, 90)), N == (20, 20, 70) and variant == 1)
     EPI, FORM = _consts()
     nf = [n + p for n in N]
     MK = [bs.assemble_1d_bands(p, bs.make_open_knots(p, n)) for n in nf]
@@ -555,6 +577,8 @@ def test_tma_matvec3d_emulated(tma_exes, tmp_path, san, p, N, variant):
               np.einsum("i,j,k->ijk", d(ms[0]), d(ms[1]), d(ms[2])))]
     if p == 3:
         cases.insert(0, ("sum", A_sum, D_sum))
+        if not FULL:
+            cases = cases[:1]                 # core set: the bench operator; single products at p = 2, 4
     om = 0.7
     run = lambda form, epi, bb, omega, **kw: _run_tma(tma_exes[san], tmp_path, p, FORM[form], EPI[epi], ms, ks, x, bb,
                                                       omega, variant, toep, **kw)
@@ -569,6 +593,8 @@ def test_tma_matvec3d_emulated(tma_exes, tmp_path, san, p, N, variant):
         if san == "tsan" or max(N) >= 200:
             continue                          # (the other epilogues share every barrier with these two)
         assert rel(run(form, "axpy", b, om)[1], b + om * yo) < tol
+        if not FULL:
+            continue
         assert rel(run(form, "axpy", None, om)[1], om * yo) < tol
         dot, y = run(form, "jacobi", b, om)
         assert rel(y, x + dr) < tol and abs(dot - np.vdot(dr, dr)) < 1e-13 * dot
