@@ -25,18 +25,18 @@ static CUresult emu_encode_tiled(CUtensorMap* out, CUtensorMapDataType, cuuint32
                                  const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                  CUtensorMapFloatOOBfill) {
-    if (rank != 3) return CUDA_ERROR_INVALID_VALUE;
+    if (rank != 2 && rank != 3) return CUDA_ERROR_INVALID_VALUE;
     // the constraints the driver enforces and the kernels rely on
-    if (((uintptr_t)base & 15) || (strides[0] & 15) || (strides[1] & 15) || box[0] > 256 || box[1] > 256)
+    if (((uintptr_t)base & 15) || (strides[0] & 15) || (rank == 3 && (strides[1] & 15)) || box[0] > 256 || box[1] > 256)
         return CUDA_ERROR_INVALID_VALUE;
     EmuTmap t;
     t.base = (const double*)base;
     for (int i = 0; i < 3; ++i) {
-        t.dims[i] = dims[i];
-        t.box[i] = box[i];
+        t.dims[i] = i < (int)rank ? dims[i] : 1;
+        t.box[i] = i < (int)rank ? box[i] : 1;
     }
     t.strides[0] = strides[0];
-    t.strides[1] = strides[1];
+    t.strides[1] = rank == 3 ? strides[1] : 0;
     memset(out, 0, sizeof(*out));
     memcpy(out, &t, sizeof(t));
     return CUDA_SUCCESS;
@@ -120,6 +120,10 @@ static inline void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, 
     EmuBar* b = (EmuBar*)bar;
     b->tx -= (int32_t)(t.box[0] * t.box[1] * 8);
     emu_bar_check(b);
+}
+
+static inline void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+    tma_load_3d(smem_dst, tmap, c0, c1, 0, bar);       // rank-2 maps are stored with a unit third extent
 }
 
 // warp vote through a per-warp exchange buffer

@@ -126,6 +126,52 @@ def tma_mv3_section(degrees=(2, 3, 4)):
     return to_host(out)
 
 
+def tma_mv2_section():
+    """The 2-D fast path: warp-autonomous TMA mat-vec (poms_matvec2d_tma.cuh, translation unit 7) behind
+    poms_kron_matvec_2d_ex, with the round-1 kernel as its fallback (plus everything else of the
+    tu0_middle_section, which shares the entry point's neighbourhood)."""
+    text = open(os.path.join(CSRC, "poms_kernels.cu")).read()
+    tma3 = open(os.path.join(CSRC, "poms_matvec3d_tma.cuh")).read()
+    tma2 = open(os.path.join(CSRC, "poms_matvec2d_tma.cuh")).read()
+    a = text.index("// deterministic grid reduction")
+    a = text.rfind("\n", 0, text.rfind("\n", 0, a)) + 1
+    b = text.index("#if POMS_TU == 6")
+    c = text.index("static int g_chunk_override = 0;")
+    d = text.index("#endif", c)
+    c2 = text.index("// axis-1 chunk of the 2-D TMA kernel")
+    d2 = text.index("#endif", c2)
+    out = text[a:b] + text[c:d] + text[c2:d2]
+    # mbarrier wrappers (stripped: emu_tma.h) and the driver-entry-point / cache-key helpers of the 3-D header
+    h0 = tma3.index("struct MV3T {")
+    h1 = tma3.index("#if POMS_TU >= 1 && POMS_TU <= 5")
+    out += _strip_functions(tma3[h0:h1], ["mbar_init", "mbar_expect_tx", "mbar_wait", "tma_load_3d"])
+    k0 = tma3.index("#include <unordered_map>")
+    k1 = tma3.index("static int get_tmap(")
+    out += tma3[k0:k1]
+    # 2-D header: declarations, device section (translation unit 7), host section
+    p0 = tma2.index("struct MV2T {")
+    p1 = tma2.index("#if POMS_TU == 7")
+    out += tma2[p0:p1]
+    d0 = tma2.index("\n", p1) + 1
+    d1 = tma2.index("#endif  // POMS_TU == 7")
+    dev = _strip_functions(tma2[d0:d1], ["tma_load_2d"])
+    dev = re.sub(r'[ \t]*asm volatile\("fence[^\n]*\n', "", dev)
+    assert "asm volatile" not in dev
+    dev = re.sub(r"extern __shared__ __align__\(1024\) unsigned char smem_raw2\[\];",
+                 "alignas(1024) static unsigned char smem_raw2[EMU_DYN_SMEM_DOUBLES * 8];", dev)
+    out += dev
+    t0 = tma2.index("#if POMS_TU == 0")
+    t0 = tma2.index("\n", t0) + 1
+    t1 = tma2.index("#endif", t0)
+    out += tma2[t0:t1]
+    e = text.index("// K1: Kronecker banded mat-vec, 2-D.")
+    e = text.rfind("\n", 0, text.rfind("\n", 0, e)) + 1
+    f = text.index("// K4: dgbtrs along one axis")
+    f = text.rfind("\n", 0, text.rfind("\n", 0, f)) + 1
+    out += text[e:f]
+    return to_host(out)
+
+
 if __name__ == "__main__":
     s, n = band_solve_section()
     print(s[:400])

@@ -24,7 +24,7 @@ EMU = os.path.join(ROOT, "tests", "host_emu")
 # POMS_EMU_FULL=1 runs every case under both sanitizers (profiles/r02_host_emulation_kernels.txt is such a
 # run; it takes 3 to 10 minutes depending on the machine: 256 OS threads per emulated block).
 FULL = os.environ.get("POMS_EMU_FULL") == "1"
-TSAN_PROGS = ("emu_matvec3d_tma", "emu_transfer")
+TSAN_PROGS = ("emu_matvec3d_tma", "emu_matvec2d_tma", "emu_transfer")
 
 
 def _core(san, core_asan, core_tsan=False):
@@ -37,7 +37,7 @@ def _core(san, core_asan, core_tsan=False):
 
 @pytest.fixture(scope="module")
 def emu_builds(tmp_path_factory):
-    """The ten executables ({TMA 3-D mat-vec, transfer, band solve, generic 3-D mat-vec, 2-D mat-vec +
+    """The twelve executables ({TMA 3-D mat-vec, TMA 2-D mat-vec, transfer, band solve, generic 3-D mat-vec, 2-D mat-vec +
     vector algebra} x {ASan, TSan}), compiled in parallel; -O0: the runs are short and the harnesses have up to 150 template instantiations."""
     import sys
     gxx = shutil.which("g++")
@@ -57,10 +57,12 @@ def emu_builds(tmp_path_factory):
     (d / "tu0_middle_emu.cuh").write_text(src)
     src, nlaunch = make_emu_source.tma_mv3_section((2, 3, 4))
     (d / "mv3_tma_emu.cuh").write_text(src)
+    src, nlaunch = make_emu_source.tma_mv2_section()
+    (d / "mv2_tma_emu.cuh").write_text(src)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     procs = {}
-    for prog in ("emu_matvec3d_tma", "emu_transfer", "emu_bandsolve", "emu_matvec3d", "emu_tu0"):
-        if prog == "emu_matvec3d_tma" and not os.path.exists(os.path.join(cuda_inc, "cuda.h")):
+    for prog in ("emu_matvec3d_tma", "emu_matvec2d_tma", "emu_transfer", "emu_bandsolve", "emu_matvec3d", "emu_tu0"):
+        if "_tma" in prog and not os.path.exists(os.path.join(cuda_inc, "cuda.h")):
             continue
         for name, flags in (("asan", ["-fsanitize=address", "-fno-omit-frame-pointer"]),
                             ("tsan", ["-fsanitize=thread"])):
@@ -100,6 +102,13 @@ def tma_exes(emu_builds):
     if ("emu_matvec3d_tma", "asan") not in emu_builds:
         pytest.skip("no <cuda.h> (the emulation uses the real CUtensorMap type)")
     return {san: emu_builds.get(("emu_matvec3d_tma", san)) for san in ("asan", "tsan")}
+
+
+@pytest.fixture(scope="module")
+def tma2_exes(emu_builds):
+    if ("emu_matvec2d_tma", "asan") not in emu_builds:
+        pytest.skip("no <cuda.h> (the emulation uses the real CUtensorMap type)")
+    return {san: emu_builds.get(("emu_matvec2d_tma", san)) for san in ("asan", "tsan")}
 
 
 @pytest.fixture(scope="module")
@@ -598,3 +607,84 @@ def test_tma_matvec3d_emulated(tma_exes, tmp_path, san, p, N, variant):
         assert rel(run(form, "axpy", None, om)[1], om * yo) < tol
         dot, y = run(form, "jacobi", b, om)
         assert rel(y, x + dr) < tol and abs(dot - np.vdot(dr, dr)) < 1e-13 * dot
+
+
+# ------------------------------------------------------------------------------------------------
+# the 2-D fast path (BASELINE configs C2 and C4): warp-autonomous TMA mat-vec (kron_matvec2d_tma_kernel,
+# translation unit 7: private 4-stage ring of 2-D boxes per warp, no CTA barrier in the march) through
+# poms_kron_matvec_2d_ex with the product's own tensor-map / Toeplitz / chunking host code
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("p,N", [(3, (40, 150)), (5, (30, 300)), (2, (64, 64)), (3, (12, 515)), (1, (20, 70)),
+                                 (4, (50, 129))])
+def test_tma_matvec2d_emulated(tma2_exes, tmp_path, san, p, N):
+    _core(san, p in (3, 5) and N[0] >= 30, (p, N) == (3, (40, 150)))
+    EPI, FORM = _consts()
+    nf = [n + p for n in N]
+    MK = [bs.assemble_1d_bands(p, bs.make_open_knots(p, n)) for n in nf]
+    ms, ks = [m for m, k in MK], [k for m, k in MK]
+    ks[1] = ks[1] + ms[1]
+    W = 2 * p + 1
+    coef, rg = np.zeros((2, 2, W)), np.zeros(4, dtype=np.int32)
+    for a in range(2):                       # stencil.KronSumMatrix._toeplitz
+        m, k = ms[a], ks[a]
+        mid = m.shape[0] // 2
+        same = np.all(m == m[mid], axis=1) & np.all(k == k[mid], axis=1)
+        lo, hi = mid, mid + 1
+        while lo > 0 and same[lo - 1]:
+            lo -= 1
+        while hi < m.shape[0] and same[hi]:
+            hi += 1
+        coef[a, 0], coef[a, 1], rg[2 * a], rg[2 * a + 1] = m[mid], k[mid], lo, hi
+    rng = np.random.default_rng(p)
+    x, b = rng.standard_normal(nf), rng.standard_normal(nf)
+    n1, n2 = nf
+    ld = n2 + (n2 & 1)
+    pit = lambda a: np.pad(a, ((0, 0), (0, ld - n2)))
+
+    def run(form, epi, bb, omega, toep=True, has_dot=True):
+        hdr = np.zeros(16, dtype=np.int32)
+        hdr[:10] = [p, FORM[form], EPI[epi], n1, n2, ld, 1, 0 if bb is None else 1, 1 if has_dot else 0, 1 if toep else 0]
+        fi, fo = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+        with open(fi, "wb") as f:
+            hdr.tofile(f)
+            np.array([omega]).tofile(f)
+            for a in range(2):
+                np.ascontiguousarray(ms[a]).tofile(f)
+                np.ascontiguousarray(ks[a]).tofile(f)
+            if toep:
+                coef.tofile(f)
+                rg.tofile(f)
+            pit(x).tofile(f)
+            if bb is not None:
+                pit(bb).tofile(f)
+        env = dict(os.environ, TSAN_OPTIONS="exitcode=66", ASAN_OPTIONS="detect_leaks=0")
+        r = subprocess.run([tma2_exes[san], fi, fo], capture_output=True, text=True, env=env, timeout=900)
+        assert r.returncode == 0 and not r.stderr.strip(), (r.returncode, r.stderr[-4000:])
+        raw = open(fo, "rb").read()
+        assert np.frombuffer(raw[:4], dtype=np.int32)[0] == 0
+        dot, ntma = np.frombuffer(raw[8:24], dtype=np.float64)
+        assert ntma > 0, "the TMA path was not taken"
+        y = np.frombuffer(raw[24:], dtype=np.float64).reshape(n1, ld)
+        assert not y[:, n2:].any()
+        return dot, y[:, :n2]
+
+    ab, d = po.apply_band, (lambda B: B[:, p])
+    om = 0.7
+    for form, A, D in (("sum", lambda v: ab(ks[0], ab(ms[1], v, 1), 0) + ab(ms[0], ab(ks[1], v, 1), 0),
+                        np.outer(d(ks[0]), d(ms[1])) + np.outer(d(ms[0]), d(ks[1]))),
+                       ("single", lambda v: ab(ms[0], ab(ms[1], v, 1), 0), np.outer(d(ms[0]), d(ms[1])))):
+        yo = A(x)
+        dr = om * (b - yo) / D
+        tol = 3e-14                           # (the sum form uses the mean of the two halves of a symmetric row)
+        dot, y = run(form, "store", None, 1.0)
+        assert rel(y, yo) < tol and abs(dot - np.vdot(x, yo)) < 1e-13 * np.vdot(np.abs(x), np.abs(yo))
+        dot, y = run(form, "resid", b, 1.0)
+        assert rel(y, b - yo) < tol and abs(dot - np.vdot(b - yo, b - yo)) < 1e-12 * dot
+        if san == "tsan" and not FULL:
+            continue
+        dot, y = run(form, "jacobi", b, om)
+        assert rel(y, x + dr) < tol and abs(dot - np.vdot(dr, dr)) < 1e-12 * dot
+        assert rel(run(form, "dinv", b, om, has_dot=False)[1], dr) < tol
+        assert rel(run(form, "axpy", b, om)[1], b + om * yo) < tol
+        assert rel(run(form, "store", None, 1.0, toep=False)[1], yo) < tol      # no Toeplitz hints
