@@ -21,7 +21,7 @@ def section(path, start_marker, end_marker):
 
 def to_host(src):
     src = src.replace("\\\n", " ")                             # join macro continuation lines
-    launch = re.compile(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)<<<([^;]*?)>>>\(([^;()]*)\)")
+    launch = re.compile(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)<<<([^;]*?)>>>\(((?:[^;()]|\([^;()]*\))*)\)")
     src, n = launch.subn(lambda m: "EMU_LAUNCH_EX((%s), %s, %s)" % (m.group(1), m.group(2), m.group(3)), src)
     assert "<<<" not in src, "unconverted launch"
     src = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"static \1 \2[EMU_DYN_SMEM_DOUBLES];", src)
@@ -32,6 +32,16 @@ def band_solve_section():
     src = section(os.path.join(CSRC, "poms_kernels.cu"), "// K4: dgbtrs along one axis",
                   "// K5: per-axis sparse row gather")
     return to_host(src)
+
+
+def axis_gather_section():
+    """Per-axis sparse row gather (2-D transfers, fallback of the 3-D ones, slab-plan rows)."""
+    text = open(os.path.join(CSRC, "poms_kernels.cu")).read()
+    a = text.index("// K5: per-axis sparse row gather")
+    a = text.rfind("\n", 0, text.rfind("\n", 0, a)) + 1
+    b = text.index("// dense mat-vec for the replicated coarse solve")
+    b = text.rfind("\n", 0, text.rfind("\n", 0, b)) + 1
+    return to_host(text[a:b])
 
 
 def generic_mv3_section():

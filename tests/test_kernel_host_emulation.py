@@ -59,15 +59,19 @@ def emu_builds(tmp_path_factory):
     (d / "mv3_tma_emu.cuh").write_text(src)
     src, nlaunch = make_emu_source.tma_mv2_section()
     (d / "mv2_tma_emu.cuh").write_text(src)
+    src, nlaunch = make_emu_source.axis_gather_section()
+    assert nlaunch == 3
+    (d / "axis_gather_emu.cuh").write_text(src)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     procs = {}
-    for prog in ("emu_matvec3d_tma", "emu_matvec2d_tma", "emu_transfer", "emu_bandsolve", "emu_matvec3d", "emu_tu0"):
+    for prog in ("emu_matvec3d_tma", "emu_matvec2d_tma", "emu_transfer", "emu_bandsolve", "emu_matvec3d", "emu_tu0",
+                 "emu_axis_gather"):
         if "_tma" in prog and not os.path.exists(os.path.join(cuda_inc, "cuda.h")):
             continue
         for name, flags in (("asan", ["-fsanitize=address", "-fno-omit-frame-pointer"]),
                             ("tsan", ["-fsanitize=thread"])):
-            if name == "tsan" and not FULL and prog not in TSAN_PROGS:
-                continue
+            if name == "tsan" and ((not FULL and prog not in TSAN_PROGS) or prog == "emu_axis_gather"):
+                continue                      # (the gather kernels have no barrier and no shared memory)
             out = str(d / (prog + "_" + name))
             procs[prog, name] = (out, subprocess.Popen(
                 [gxx, "-std=c++17", "-O0", "-g"] + flags + ["-I" + EMU, "-I" + str(d), "-I" + os.path.join(ROOT, "include"),
@@ -688,3 +692,84 @@ def test_tma_matvec2d_emulated(tma2_exes, tmp_path, san, p, N):
         assert rel(run(form, "dinv", b, om, has_dot=False)[1], dr) < tol
         assert rel(run(form, "axpy", b, om)[1], b + om * yo) < tol
         assert rel(run(form, "store", None, 1.0, toep=False)[1], yo) < tol      # no Toeplitz hints
+
+
+# ------------------------------------------------------------------------------------------------
+# poms_axis_gather (section K5): the per-axis sparse row gather behind the 2-D transfers, the fallback of
+# the 3-D ones and the slab-plan rows (negative starts); address sanitizer only: no barrier, no shared memory
+# ------------------------------------------------------------------------------------------------
+def _gather(exe, tmp, start, coef, n_in, src, axis, acc=None):
+    shape = list(src.shape)
+    nd, n_out, W = len(shape), len(start), coef.shape[1]
+    out_shape = list(shape)
+    out_shape[axis] = n_out
+    ld = shape[-1]
+    if axis == nd - 1:
+        ld_out = n_out + (n_out & 1)
+        out_shape[-1] = ld_out
+        geo = [int(np.prod(shape[:-1])), ld, 1, ld_out, 1, 1]
+    elif axis == 0:
+        rest = int(np.prod(shape[1:]))
+        geo = [1, 0, rest, 0, rest, rest]
+    else:
+        geo = [shape[0], shape[1] * ld, ld, n_out * ld, ld, ld]
+    out0 = np.zeros(out_shape) if acc is None else acc.copy()
+    hdr = np.zeros(16, dtype=np.int32)
+    hdr[:5] = [W, n_in, n_out, 0 if acc is None else 1, n_out]
+    fi, fo = str(tmp / "in.bin"), str(tmp / "out.bin")
+    with open(fi, "wb") as f:
+        hdr.tofile(f)
+        np.array(geo, dtype=np.int64).tofile(f)
+        np.array([src.size, out0.size], dtype=np.int64).tofile(f)
+        np.ascontiguousarray(start, dtype=np.int32).tofile(f)
+        np.ascontiguousarray(coef).tofile(f)
+        np.ascontiguousarray(src).tofile(f)
+        np.ascontiguousarray(out0).tofile(f)
+    r = subprocess.run([exe, fi, fo], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert r.returncode == 0 and not r.stderr.strip(), (r.returncode, r.stderr[-4000:])
+    raw = open(fo, "rb").read()
+    assert np.frombuffer(raw[:4], dtype=np.int32)[0] == 0
+    return np.frombuffer(raw[4:], dtype=np.float64).reshape(out_shape)
+
+
+def _gather_ref(start, coef, n_in, src, axis):
+    n_out, W = coef.shape
+    A = np.zeros((n_out, n_in))
+    for i in range(n_out):
+        for w in range(W):
+            if 0 <= start[i] + w < n_in:
+                A[i, start[i] + w] += coef[i, w]
+    return np.moveaxis(np.tensordot(A, src, axes=(1, axis)), 0, axis)
+
+
+@pytest.mark.parametrize("p,n", [(3, 16), (2, 40), (5, 130)])
+def test_axis_gather_emulated(emu_builds, tmp_path, p, n):
+    from poms_b200.dist import slab_transfer_plan
+    _core("asan", p == 3)
+    exe = emu_builds["emu_axis_gather", "asan"]
+    nf, nc = n + p, n // 2 + p
+    st, cf, _ = bs.knot_insertion_rows(bs.make_open_knots(p, nc), bs.make_open_knots(p, nf), p)
+    rng = np.random.default_rng(n)
+    for rest in [(7,), (3, 130), (66,)]:
+        for axis in range(len(rest) + 1):
+            shp = list(rest)
+            shp.insert(axis, nc)
+            last = shp[-1]
+            src = np.zeros(shp[:-1] + [last + (last & 1)])
+            src[..., :last] = rng.standard_normal(shp)
+            lastax = axis == len(shp) - 1
+            cut = (lambda a: a[..., :nf]) if lastax else (lambda a: a)
+            r = _gather_ref(st, cf, nc, src[..., :last] if lastax else src, axis)
+            y = _gather(exe, tmp_path, st, cf, nc, src, axis)
+            assert rel(cut(y), cut(r)) < 1e-14
+            acc = rng.standard_normal(y.shape)
+            if lastax:
+                acc[..., nf:] = 0
+            assert rel(cut(_gather(exe, tmp_path, st, cf, nc, src, axis, acc=acc) - acc), cut(r)) < 1e-13
+    plan = slab_transfer_plan(st, cf, nc, 3, True)
+    assert min(pl[0].min() for pl in plan["P0"]) < 0
+    for q in range(3):
+        s0, c0, n_in = plan["P0"][q]
+        src = rng.standard_normal((n_in, 5, 66))
+        assert rel(_gather(exe, tmp_path, s0, c0, n_in, src, 0), _gather_ref(s0, c0, n_in, src, 0)) < 1e-14
