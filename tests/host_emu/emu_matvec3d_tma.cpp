@@ -4,7 +4,7 @@
 // creation, Toeplitz tables, variant selection and chunking are the product's own host code.
 //   emu_matvec3d_tma <in> <out>
 // in:  int32 header (16): {p, form, epi, n1, n2, n3, ld, variant, has_b, has_dot, has_toep, force_generic,
-//      dot_with, 0...}, fp64 omega, bands m1 k1 m2 k2 m3 k3, toep coefficients (3*2*(2p+1) fp64) and
+//      dot_with, glo, ghi, 0} (x, and z, then hold glo + n1 + ghi planes: ghost planes of a slab), fp64 omega, bands m1 k1 m2 k2 m3 k3, toep coefficients (3*2*(2p+1) fp64) and
 //      ranges (6 int32) if has_toep, x (n1*n2*ld), b (if has_b), z (if dot_with)
 // out: int32 status, int32 fused flag, fp64 dot, fp64 number of emulated TMA copies, y
 #define POMS_HOST_EMU 1
@@ -39,6 +39,7 @@ int main(int argc, char** argv) {
     rdinto(f, h, sizeof(h));
     const int p = h[0], form = h[1], epi = h[2], n1 = h[3], n2 = h[4], n3 = h[5], ld = h[6], variant = h[7];
     const int has_b = h[8], has_dot = h[9], has_toep = h[10], force_generic = h[11], dot_with = h[12], W = 2 * p + 1;
+    const int glo = h[13], ghi = h[14];
     double om;
     rdinto(f, &om, 8);
     const int na[3] = {n1, n2, n3};
@@ -55,11 +56,11 @@ int main(int argc, char** argv) {
         rdinto(f, toep, (size_t)3 * 2 * W * 8);
         rdinto(f, rng, sizeof(rng));
     }
-    const size_t total = (size_t)n1 * n2 * ld;
-    Buf x(total), b(has_b ? total : 0), z(dot_with ? total : 0), y(total);
-    rdinto(f, x.p, total * 8);
+    const size_t total = (size_t)n1 * n2 * ld, pl = (size_t)n2 * ld, totg = (size_t)(n1 + glo + ghi) * pl;
+    Buf x(totg), b(has_b ? total : 0), z(dot_with ? totg : 0), y(total);
+    rdinto(f, x.p, totg * 8);
     if (has_b) rdinto(f, b.p, total * 8);
-    if (dot_with) rdinto(f, z.p, total * 8);
+    if (dot_with) rdinto(f, z.p, totg * 8);
     fclose(f);
     for (size_t i = 0; i < total; ++i) y.p[i] = 0.0;
     const size_t wsn = POMS_WS_HEADER + (size_t)POMS_MAX_PARTIALS * 8;
@@ -69,10 +70,10 @@ int main(int argc, char** argv) {
     int fused = 0;
     poms_set_matvec3d_variant(variant);
     poms_set_force_generic(force_generic);
-    const int rc = poms_kron_matvec_3d_dotv(x.p, y.p, has_b ? b.p : nullptr, n1, n2, n3, ld, (int64_t)n2 * ld, 0, 0, p,
+    const int rc = poms_kron_matvec_3d_dotv(x.p + glo * pl, y.p, has_b ? b.p : nullptr, n1, n2, n3, ld, (int64_t)pl, glo, ghi, p,
                                             form, m[0]->p, k[0]->p, m[1]->p, k[1]->p, m[2]->p, k[2]->p, epi, om,
                                             has_dot ? &dot : nullptr, ws.get(), nullptr, has_toep ? toep : nullptr,
-                                            has_toep ? rng : nullptr, dot_with ? z.p : nullptr, &fused);
+                                            has_toep ? rng : nullptr, dot_with ? z.p + glo * pl : nullptr, &fused);
     if (rc != 0) fprintf(stderr, "status %d: %s\n", rc, g_err);
     FILE* o = fopen(argv[2], "wb");
     const int32_t rc32 = rc, fu = fused;

@@ -529,13 +529,15 @@ def _toeplitz_tables(ms, ks, p):
     return coef, rng
 
 
-def _run_tma(exe, tmp, p, form, epi, ms, ks, x, b, omega, variant, toep, has_dot=True):
+def _run_tma(exe, tmp, p, form, epi, ms, ks, x, b, omega, variant, toep, has_dot=True, glo=0, ghi=0):
+    """x holds glo + n1 + ghi planes (ghost planes of a slab sub-problem); the result has n1 planes."""
     n1, n2, n3 = x.shape
+    n1 -= glo + ghi
     ld = n3 + (n3 & 1)
     pit = lambda a: np.pad(a, ((0, 0), (0, 0), (0, ld - n3)))
     hdr = np.zeros(16, dtype=np.int32)
-    hdr[:13] = [p, form, epi, n1, n2, n3, ld, variant, 0 if b is None else 1, 1 if has_dot else 0,
-                0 if toep is None else 1, 0, 0]
+    hdr[:15] = [p, form, epi, n1, n2, n3, ld, variant, 0 if b is None else 1, 1 if has_dot else 0,
+                0 if toep is None else 1, 0, 0, glo, ghi]
     fi, fo = str(tmp / "in.bin"), str(tmp / "out.bin")
     with open(fi, "wb") as f:
         hdr.tofile(f)
@@ -773,3 +775,38 @@ def test_axis_gather_emulated(emu_builds, tmp_path, p, n):
         s0, c0, n_in = plan["P0"][q]
         src = rng.standard_normal((n_in, 5, 66))
         assert rel(_gather(exe, tmp_path, s0, c0, n_in, src, 0), _gather_ref(s0, c0, n_in, src, 0)) < 1e-14
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("variant", [1, 0])
+def test_tma_matvec3d_emulated_on_slab_subproblems(tma_exes, tmp_path, san, variant):
+    """The multi-GPU form of the hot kernel: axis 1 cut into three slabs, every rank's sub-problem with
+    its ghost planes (glo / ghi = p; the tensor maps cover owned + ghost planes, the axis-1 band rows and
+    the Toeplitz range are the slab's: stencil.KronSumMatrix._launch), against the global operator."""
+    _core(san, variant == 1)
+    EPI, FORM = _consts()
+    p, N = 3, (60, 20, 70)
+    nf = [n + p for n in N]
+    MK = [bs.assemble_1d_bands(p, bs.make_open_knots(p, n)) for n in nf]
+    ms, ks = [m for m, k in MK], [k for m, k in MK]
+    ks[2] = ks[2] + ms[2]
+    coef, rg = _toeplitz_tables(ms, ks, p)
+    rng = np.random.default_rng(0)
+    xg, bg = rng.standard_normal(nf), rng.standard_normal(nf)
+    ab = po.apply_band
+    yo = (ab(ks[0], ab(ms[1], ab(ms[2], xg, 2), 1), 0) + ab(ms[0], ab(ks[1], ab(ms[2], xg, 2), 1), 0)
+          + ab(ms[0], ab(ms[1], ab(ks[2], xg, 2), 1), 0))
+    for s, e in ((0, 20), (21, 41), (42, 62)):
+        n1 = e - s + 1
+        glo, ghi = (p if s > 0 else 0), (p if e < nf[0] - 1 else 0)
+        r = rg.copy()
+        r[0] = max(0, int(rg[0]) - s)
+        r[1] = max(int(r[0]), min(n1, int(rg[1]) - s))
+        ms_l, ks_l = [ms[0][s:e + 1], ms[1], ms[2]], [ks[0][s:e + 1], ks[1], ks[2]]
+        run = lambda epi, bb, om: _run_tma(tma_exes[san], tmp_path, p, FORM["sum"], EPI[epi], ms_l, ks_l,
+                                           xg[s - glo:e + ghi + 1], bb, om, variant, (coef, r), glo=glo, ghi=ghi)
+        dot, y = run("store", None, 1.0)
+        assert rel(y, yo[s:e + 1]) < 1e-14
+        assert abs(dot - np.vdot(xg[s:e + 1], yo[s:e + 1])) < 1e-13 * np.vdot(np.abs(xg[s:e + 1]), np.abs(yo[s:e + 1]))
+        assert rel(run("resid", bg[s:e + 1], 1.0)[1], (bg - yo)[s:e + 1]) < 1e-14
+        assert rel(run("axpy", bg[s:e + 1], 0.7)[1], (bg + 0.7 * yo)[s:e + 1]) < 1e-14
