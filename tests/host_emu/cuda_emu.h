@@ -3,6 +3,12 @@
 // block, blocks one after the other, __syncthreads() = pthread barrier, __shared__ = function-local
 // static.  Built with -fsanitize=address or -fsanitize=thread, so that out-of-bounds accesses and
 // missing barriers of the kernel show up on a machine without a GPU.  Never part of libpoms_b200.so.
+// Limits: (1) the threads of a warp run independently, so code that relies on implicit warp lockstep
+// without __syncwarp() is reported as a race (conservative); (2) static shared arrays keep their content
+// from one block to the next (an uninitialised read could be masked); dynamic shared memory is one
+// global buffer whose tail beyond the requested size is poisoned under the address sanitizer, so a
+// carve-up that overruns the launch's byte count is caught; (3) cp.async waits and the memory model
+// below block scope are not modelled; (4) timing means nothing.
 #pragma once
 #include <pthread.h>
 
@@ -33,6 +39,11 @@ constexpr int cudaSuccess = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8;
 template <class K>
 static inline int cudaFuncSetAttribute(K, int, int) { return 0; }
 constexpr int EMU_DYN_SMEM_DOUBLES = 28 * 1024;   // 224 KB, the most a kernel can ask for
+alignas(1024) static unsigned char emu_dyn_smem[EMU_DYN_SMEM_DOUBLES * 8];   // `extern __shared__` of every kernel
+#if defined(__SANITIZE_ADDRESS__)
+extern "C" void __asan_poison_memory_region(void const volatile*, size_t);
+extern "C" void __asan_unpoison_memory_region(void const volatile*, size_t);
+#endif
 static char g_err[256];
 static long long g_launches;
 
@@ -89,13 +100,24 @@ static inline void cp_async_wait() {}
 #define POMS_LAUNCH(kernel, grid, stream, arg) emu_launch(grid, [&] { kernel(arg); })
 
 // launch with an explicit block size and argument list (sources rewritten by make_emu_source.py)
+#ifndef EMU_SMEM_SHRINK
+#define EMU_SMEM_SHRINK 0     // self-test of the poisoning: -DEMU_SMEM_SHRINK=64 must make a kernel that uses
+#endif                        // all of its dynamic shared memory fail under the address sanitizer
 #define EMU_LAUNCH_EX(kernel, grid, block, smem, stream, ...) \
-    emu_launch(dim3(grid), [&] { kernel(__VA_ARGS__); }, block)
+    emu_launch(dim3(grid), [&] { kernel(__VA_ARGS__); }, block, (size_t)(smem) - ((smem) ? EMU_SMEM_SHRINK : 0))
 
 constexpr int EMU_BLOCK = 256;
 template <class F>
-static void emu_launch(dim3 grid, F body, int nthreads = EMU_BLOCK) {
+static void emu_launch(dim3 grid, F body, int nthreads = EMU_BLOCK, size_t dyn_smem = 0) {
     const int EMU_BLOCK = nthreads;               // (shadows the default: the code below is unchanged)
+#if defined(__SANITIZE_ADDRESS__)
+    // dynamic shared memory: exactly the bytes of this launch are addressable
+    const size_t live = (dyn_smem + 7) & ~(size_t)7;
+    __asan_unpoison_memory_region(emu_dyn_smem, sizeof(emu_dyn_smem));
+    if (live < sizeof(emu_dyn_smem)) __asan_poison_memory_region(emu_dyn_smem + live, sizeof(emu_dyn_smem) - live);
+#else
+    (void)dyn_smem;
+#endif
     blockDim = dim3(nthreads);
     gridDim = grid;
     // a warp whose threads all leave the kernel early must not block the others: the block barrier

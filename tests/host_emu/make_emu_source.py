@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY: cut a kernel section out of poms_b200/csrc/poms_kernels.cu and rewrite the
 CUDA-only syntax so that g++ can compile it over cuda_emu.h:
     kernel<T...><<<grid, block, smem, stream>>>(args)  ->  EMU_LAUNCH_EX((kernel<T...>), grid, block, smem, stream, args)
-    extern __shared__ double name[];                      ->  static double name[EMU_DYN_SMEM_DOUBLES];
+    extern __shared__ T name[];                           ->  T* const name = reinterpret_cast<T*>(emu_dyn_smem);
 The product source is not modified; the output goes to a temporary directory of the test."""
 import os
 import re
@@ -24,7 +24,9 @@ def to_host(src):
     launch = re.compile(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)<<<([^;]*?)>>>\(((?:[^;()]|\([^;()]*\))*)\)")
     src, n = launch.subn(lambda m: "EMU_LAUNCH_EX((%s), %s, %s)" % (m.group(1), m.group(2), m.group(3)), src)
     assert "<<<" not in src, "unconverted launch"
-    src = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"static \1 \2[EMU_DYN_SMEM_DOUBLES];", src)
+    src = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?((?:unsigned\s+)?\w+)\s+(\w+)\[\];",
+                 r"\1* const \2 = reinterpret_cast<\1*>(emu_dyn_smem);", src)
+    assert "extern __shared__" not in src
     return src, n
 
 
@@ -113,8 +115,6 @@ def tma_mv3_section(degrees=(2, 3, 4)):
     dev = tma[d0:d1].replace('#include "poms_matvec3d_v3.cuh"', _strip_functions(v3, ["mbar_arrive"]))
     dev = re.sub(r'[ \t]*asm volatile\("fence[^\n]*\n', "", dev)
     assert "asm volatile" not in dev
-    dev = re.sub(r"extern __shared__ __align__\(1024\) unsigned char smem_raw\[\];",
-                 "alignas(1024) static unsigned char smem_raw[EMU_DYN_SMEM_DOUBLES * 8];", dev)
     sig = ("(const CUtensorMap* tm3, const MV3T& g, int form, int epi, int variant, int ntiles, dim3 grid, "
            "cudaStream_t st)")
     for P in range(1, 6):
@@ -167,8 +167,6 @@ def tma_mv2_section():
     dev = _strip_functions(tma2[d0:d1], ["tma_load_2d"])
     dev = re.sub(r'[ \t]*asm volatile\("fence[^\n]*\n', "", dev)
     assert "asm volatile" not in dev
-    dev = re.sub(r"extern __shared__ __align__\(1024\) unsigned char smem_raw2\[\];",
-                 "alignas(1024) static unsigned char smem_raw2[EMU_DYN_SMEM_DOUBLES * 8];", dev)
     out += dev
     t0 = tma2.index("#if POMS_TU == 0")
     t0 = tma2.index("\n", t0) + 1
