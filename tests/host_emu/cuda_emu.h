@@ -71,6 +71,23 @@ static inline double __shfl_xor_sync(unsigned, double v, int o) {
     __syncwarp();
     return r;
 }
+// mma.sync.aligned.m8n8k4.row.col.f64: D (8 x 8) += A (8 x 4, row major) * B (4 x 8, column major).  Fragment
+// layout of the PTX ISA: lane l holds A[l / 4][l % 4], B[l % 4][l / 4] and D[l / 4][2 * (l % 4) + {0, 1}].
+static double emu_mma_a[32][32], emu_mma_b[32][32];
+static inline void dmma8x8x4(double& d0, double& d1, double a, double b) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    emu_mma_a[w][lane] = a;
+    emu_mma_b[w][lane] = b;
+    __syncwarp();
+    const int row = lane >> 2, col = 2 * (lane & 3);
+    for (int k = 0; k < 4; ++k) {
+        const double av = emu_mma_a[w][row * 4 + k];
+        d0 = std::fma(av, emu_mma_b[w][col * 4 + k], d0);
+        d1 = std::fma(av, emu_mma_b[w][(col + 1) * 4 + k], d1);
+    }
+    __syncwarp();
+}
+static inline int cudaGetLastError() { return 0; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 template <class T>

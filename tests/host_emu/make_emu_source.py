@@ -46,6 +46,18 @@ def axis_gather_section():
     return to_host(text[a:b])
 
 
+def dmma_section():
+    """Dense per-axis contraction on the fp64 tensor cores (poms_extra.cu): the coarse solve of the bench.
+    The one-instruction wrapper dmma8x8x4 (mma.sync.m8n8k4.f64) is removed; cuda_emu.h provides it with
+    the fragment layout of the PTX ISA."""
+    text = open(os.path.join(CSRC, "poms_extra.cu")).read()
+    a = text.index("// Dense per-axis contraction on the fp64 tensor cores")
+    a = text.rfind("\n", 0, text.rfind("\n", 0, a)) + 1
+    b = text.index("// Full (non-separable) 3-D stencil mat-vec")
+    b = text.rfind("\n", 0, text.rfind("\n", 0, b)) + 1
+    return to_host(_strip_functions(text[a:b], ["dmma8x8x4"]))
+
+
 def generic_mv3_section():
     """The common device helpers (deterministic grid reduction, shift-form partial sums, MV3) and the
     generic 3-D Kronecker mat-vec of translation unit 6 (the fallback for tiny or misaligned grids)."""

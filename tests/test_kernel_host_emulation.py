@@ -62,10 +62,13 @@ def emu_builds(tmp_path_factory):
     src, nlaunch = make_emu_source.axis_gather_section()
     assert nlaunch == 3
     (d / "axis_gather_emu.cuh").write_text(src)
+    src, nlaunch = make_emu_source.dmma_section()
+    assert nlaunch == 2
+    (d / "dmma_emu.cuh").write_text(src)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     procs = {}
     for prog in ("emu_matvec3d_tma", "emu_matvec2d_tma", "emu_transfer", "emu_bandsolve", "emu_matvec3d", "emu_tu0",
-                 "emu_axis_gather"):
+                 "emu_axis_gather", "emu_dmma"):
         if "_tma" in prog and not os.path.exists(os.path.join(cuda_inc, "cuda.h")):
             continue
         for name, flags in (("asan", ["-fsanitize=address", "-fno-omit-frame-pointer"]),
@@ -792,6 +795,58 @@ def test_axis_gather_emulated(emu_builds, tmp_path, p, n):
         s0, c0, n_in = plan["P0"][q]
         src = rng.standard_normal((n_in, 5, 66))
         assert rel(_gather(exe, tmp_path, s0, c0, n_in, src, 0), _gather_ref(s0, c0, n_in, src, 0)) < 1e-14
+
+
+# ------------------------------------------------------------------------------------------------
+# poms_axis_dense_dmma: the dense eigenbasis contraction of the coarse solve on the fp64 tensor cores.  The
+# kernel source runs unchanged; only the one-instruction wrapper around mma.sync.m8n8k4.f64 is replaced by
+# cuda_emu.h's lane-by-lane model of the PTX fragment layout (so a wrong fragment index in the kernel shows).
+# ------------------------------------------------------------------------------------------------
+def _dmma(exe, tmp, Q, src, axis):
+    shape = list(src.shape)
+    n_out, n_in = Q.shape
+    assert shape[axis] == n_in and len(shape) == 3
+    out_shape = list(shape)
+    out_shape[axis] = n_out
+    if axis == 2:
+        geo = [shape[0] * shape[1], n_in, 1, n_out, 1, 1]
+    elif axis == 0:
+        rest = shape[1] * shape[2]
+        geo = [1, 0, rest, 0, rest, rest]
+    else:
+        geo = [shape[0], n_in * shape[2], shape[2], n_out * shape[2], shape[2], shape[2]]
+    hdr = np.zeros(16, dtype=np.int32)
+    hdr[:2] = [n_in, n_out]
+    fi, fo = str(tmp / "in.bin"), str(tmp / "out.bin")
+    with open(fi, "wb") as f:
+        hdr.tofile(f)
+        np.array(geo, dtype=np.int64).tofile(f)
+        np.array([src.size, int(np.prod(out_shape))], dtype=np.int64).tofile(f)
+        np.ascontiguousarray(Q).tofile(f)
+        np.ascontiguousarray(src).tofile(f)
+    r = subprocess.run([exe, fi, fo], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert r.returncode == 0 and not r.stderr.strip(), (r.returncode, r.stderr[-4000:])
+    raw = open(fo, "rb").read()
+    assert np.frombuffer(raw[:4], dtype=np.int32)[0] == 0
+    return np.frombuffer(raw[4:], dtype=np.float64).reshape(out_shape)
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("shape,n_out", [((19, 70, 9), None), ((35, 33, 67), None), ((8, 5, 130), 11)])
+def test_dense_dmma_contraction_emulated(emu_builds, tmp_path, san, shape, n_out):
+    """Square (the eigenbasis Q and Q^T of the coarse solve) and rectangular Q along each of the three axes, extents
+    that are not multiples of the 64 x 64 x 32 tile: exact against numpy to rounding, no out-of-bounds access,
+    no race between the staging loops and the fragment loads."""
+    _core(san, shape[0] == 19)
+    exe = _Exes(emu_builds, "emu_dmma")[san]
+    rng = np.random.default_rng(shape[1])
+    src = rng.standard_normal(shape)
+    for axis in range(3):
+        m = n_out or shape[axis]
+        Q = rng.standard_normal((m, shape[axis]))
+        ref = np.moveaxis(np.tensordot(Q, src, axes=(1, axis)), 0, axis)
+        assert rel(_dmma(exe, tmp_path, Q, src, axis), ref) < 1e-14
 
 
 @pytest.mark.parametrize("san", ["asan", "tsan"])
