@@ -196,3 +196,11 @@ if __name__ == "__main__":
     s, n = band_solve_section()
     print(s[:400])
     print("...", n, "launches converted,", len(s.splitlines()), "lines")
+
+
+def setup_section():
+    """Device-side 1-D set-up kernels (poms_setup.cu): assembly by quadrature, knot-insertion rows, banded LU
+    without pivoting -- everything below the include of the common header."""
+    text = open(os.path.join(CSRC, "poms_setup.cu")).read()
+    a = text.index("#define POMS_MAXP")
+    return to_host(text[a:])

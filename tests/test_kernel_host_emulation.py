@@ -65,10 +65,13 @@ def emu_builds(tmp_path_factory):
     src, nlaunch = make_emu_source.dmma_section()
     assert nlaunch == 2
     (d / "dmma_emu.cuh").write_text(src)
+    src, nlaunch = make_emu_source.setup_section()
+    assert nlaunch == 3
+    (d / "setup_emu.cuh").write_text(src)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     procs = {}
     for prog in ("emu_matvec3d_tma", "emu_matvec2d_tma", "emu_transfer", "emu_bandsolve", "emu_matvec3d", "emu_tu0",
-                 "emu_axis_gather", "emu_dmma"):
+                 "emu_axis_gather", "emu_dmma", "emu_setup"):
         if "_tma" in prog and not os.path.exists(os.path.join(cuda_inc, "cuda.h")):
             continue
         for name, flags in (("asan", ["-fsanitize=address", "-fno-omit-frame-pointer"]),
@@ -847,6 +850,88 @@ def test_dense_dmma_contraction_emulated(emu_builds, tmp_path, san, shape, n_out
         Q = rng.standard_normal((m, shape[axis]))
         ref = np.moveaxis(np.tensordot(Q, src, axes=(1, axis)), 0, axis)
         assert rel(_dmma(exe, tmp_path, Q, src, axis), ref) < 1e-14
+
+
+# ------------------------------------------------------------------------------------------------
+# Device-side 1-D set-up (poms_setup.cu): assembly by quadrature, knot-insertion rows by the Oslo
+# recursion, banded LU without pivoting -- the same comparisons as tests/test_gpu_setup.py, on exactly sized buffers
+# ------------------------------------------------------------------------------------------------
+def _setup(exe, tmp, hdr_vals, arrays):
+    hdr = np.zeros(16, dtype=np.int32)
+    hdr[:len(hdr_vals)] = hdr_vals
+    fi, fo = str(tmp / "in.bin"), str(tmp / "out.bin")
+    with open(fi, "wb") as f:
+        hdr.tofile(f)
+        for a in arrays:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            np.array([a.size], dtype=np.int64).tofile(f)
+            a.tofile(f)
+    r = subprocess.run([exe, fi, fo], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert r.returncode == 0 and not r.stderr.strip(), (r.returncode, r.stderr[-4000:])
+    raw = open(fo, "rb").read()
+    assert np.frombuffer(raw[:4], dtype=np.int32)[0] == 0
+    return raw[4:]
+
+
+def _graded_knots(p, N, uniform):
+    T = bs.make_open_knots(p, N + p)
+    if not uniform:
+        inner = np.linspace(0.0, 1.0, N + 1)[1:-1] ** 1.7
+        T = np.concatenate([np.zeros(p + 1), inner, np.ones(p + 1)])
+    return T
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5])
+def test_setup_kernels_emulated(emu_builds, tmp_path, san, p):
+    _core(san, p == 3)
+    exe = _Exes(emu_builds, "emu_setup")[san]
+    # assembly: uniform and graded open knot vectors, n not a multiple of the block
+    for N, uniform in [(8, True), (37, True), (23, False), (150, True)]:
+        T = _graded_knots(p, N, uniform)
+        n = N + p
+        Mh, Kh = bs.assemble_1d_bands(p, T, toeplitz_interior=False)
+        u, w = np.polynomial.legendre.leggauss(p + 1)
+        raw = _setup(exe, tmp_path, [0, n, p], [T, u, w])
+        MK = np.frombuffer(raw, dtype=np.float64).reshape(2, n, 2 * p + 1)
+        assert np.abs(MK[0] - Mh).max() <= 1e-13 * np.abs(Mh).max()
+        assert np.abs(MK[1] - Kh).max() <= 1e-13 * np.abs(Kh).max()
+    # knot-insertion rows: dyadic and wider refinements, and a graded coarse vector refined by midpoints
+    cases = [(bs.make_open_knots(p, Nc + p), bs.make_open_knots(p, Nc * ratio + p))
+             for Nc, ratio in [(4, 2), (5, 4), (16, 8), (70, 2)]]
+    Tg = _graded_knots(p, 11, False)
+    br = np.unique(Tg)
+    cases.append((Tg, np.concatenate([np.zeros(p), np.sort(np.concatenate([br, 0.5 * (br[1:] + br[:-1])])), np.ones(p)])))
+    for Tc, Tf in cases:
+        sh, ch, nc = bs.knot_insertion_rows(Tc, Tf, p)
+        nf = len(Tf) - p - 1
+        raw = _setup(exe, tmp_path, [1, 0, p, nc, nf], [Tc, Tf])
+        sd = np.frombuffer(raw[:4 * nf], dtype=np.int32)
+        cd = np.frombuffer(raw[4 * nf:], dtype=np.float64).reshape(nf, p + 1)
+        assert np.array_equal(sd, sh)
+        assert np.abs(cd - ch).max() <= 1e-15
+        assert np.abs(cd.sum(axis=1) - 1.0).max() < 1e-14
+    # banded LU without pivoting against LAPACK's dgbtrf (no interchanges on these bands)
+    for n in (3 * p + 2, 67, 140):
+        band = bs.glt_band(p, n, degree=max(2 * p - 1, 1))
+        c = (band.shape[1] - 1) // 2
+        q = c
+        while q > 0 and not band[:, c - q].any():
+            q -= 1
+        band = band[:, c - q:c + q + 1]
+        lh, kl, ku, piv = bs.band_lu(band)
+        assert np.array_equal(piv, np.arange(n)) and kl == ku == q
+        raw = _setup(exe, tmp_path, [2, n, p, 0, 0, q], [band])
+        assert np.frombuffer(raw[:4], dtype=np.int32)[0] == 0
+        ab = np.frombuffer(raw[4:], dtype=np.float64).reshape(3 * q + 1, n)
+        assert np.abs(ab - lh).max() <= 1e-13 * np.abs(lh).max()
+    # a zero pivot is reported through info, not divided by
+    band = np.zeros((9, 3))
+    band[:, 1] = 1.0
+    band[4, 1] = 0.0
+    raw = _setup(exe, tmp_path, [2, 9, 1, 0, 0, 1], [band])
+    assert np.frombuffer(raw[:4], dtype=np.int32)[0] == 5
 
 
 @pytest.mark.parametrize("san", ["asan", "tsan"])
