@@ -204,3 +204,16 @@ def setup_section():
     text = open(os.path.join(CSRC, "poms_setup.cu")).read()
     a = text.index("#define POMS_MAXP")
     return to_host(text[a:])
+
+
+def stencil3d_section():
+    """Full (non-separable) 3-D stencil mat-vec and the two-colour update (poms_extra.cu), preceded by the
+    common device helpers (warp / block sums, deterministic grid reduction) of poms_kernels.cu."""
+    text = open(os.path.join(CSRC, "poms_kernels.cu")).read()
+    a = text.index("// deterministic grid reduction")
+    a = text.rfind("\n", 0, text.rfind("\n", 0, a)) + 1
+    b = text.index("#if POMS_TU == 6")
+    extra = open(os.path.join(CSRC, "poms_extra.cu")).read()
+    c = extra.index("// Full (non-separable) 3-D stencil mat-vec")
+    c = extra.rfind("\n", 0, extra.rfind("\n", 0, c)) + 1
+    return to_host(text[a:b] + extra[c:])

@@ -68,10 +68,13 @@ def emu_builds(tmp_path_factory):
     src, nlaunch = make_emu_source.setup_section()
     assert nlaunch == 3
     (d / "setup_emu.cuh").write_text(src)
+    src, nlaunch = make_emu_source.stencil3d_section()
+    assert nlaunch == 2
+    (d / "stencil3d_emu.cuh").write_text(src)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     procs = {}
     for prog in ("emu_matvec3d_tma", "emu_matvec2d_tma", "emu_transfer", "emu_bandsolve", "emu_matvec3d", "emu_tu0",
-                 "emu_axis_gather", "emu_dmma", "emu_setup"):
+                 "emu_axis_gather", "emu_dmma", "emu_setup", "emu_stencil3d"):
         if "_tma" in prog and not os.path.exists(os.path.join(cuda_inc, "cuda.h")):
             continue
         for name, flags in (("asan", ["-fsanitize=address", "-fno-omit-frame-pointer"]),
@@ -932,6 +935,78 @@ def test_setup_kernels_emulated(emu_builds, tmp_path, san, p):
     band[4, 1] = 0.0
     raw = _setup(exe, tmp_path, [2, 9, 1, 0, 0, 1], [band])
     assert np.frombuffer(raw[:4], dtype=np.int32)[0] == 5
+
+
+# ------------------------------------------------------------------------------------------------
+# poms_stencil_matvec_3d (full, non-separable 3-D stencil = spl's StencilMatrix.dot in 3-D; one warp per point,
+# shared offset table in dynamic shared memory, deterministic grid reduction) and poms_color_add
+# ------------------------------------------------------------------------------------------------
+def _stencil3d(exe, tmp, op, N, pads, ld, epi=0, has_dot=0, glo=0, ghi=0, omega=1.0, off=0, colour=0, arrays=(), has_b=0):
+    hdr = np.zeros(16, dtype=np.int32)
+    hdr[:15] = [op, N[0], N[1], N[2], pads[0], pads[1], pads[2], epi, has_dot, glo, ghi, ld, off, colour, has_b]
+    fi, fo = str(tmp / "in.bin"), str(tmp / "out.bin")
+    with open(fi, "wb") as f:
+        hdr.tofile(f)
+        np.array([omega]).tofile(f)
+        for a in arrays:
+            np.ascontiguousarray(a, dtype=np.float64).tofile(f)
+    r = subprocess.run([exe, fi, fo], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert r.returncode == 0 and not r.stderr.strip(), (r.returncode, r.stderr[-4000:])
+    raw = open(fo, "rb").read()
+    assert np.frombuffer(raw[:4], dtype=np.int32)[0] == 0
+    return np.frombuffer(raw[4:12], dtype=np.float64)[0], np.frombuffer(raw[12:], dtype=np.float64).reshape(N[0], N[1], ld)
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("N,pads,glo,ghi", [((6, 7, 9), (1, 1, 1), 0, 0), ((5, 6, 11), (2, 1, 3), 0, 0),
+                                            ((4, 9, 10), (2, 2, 2), 2, 1)])
+def test_full_stencil3d_emulated(emu_builds, tmp_path, san, N, pads, glo, ghi):
+    """Interior (check-free) and boundary points, unequal pads per axis, odd last extent (pad column), ghost planes
+    below and above (the slab form), every epilogue with its fused reduction."""
+    _core(san, pads == (2, 1, 3))
+    exe = _Exes(emu_builds, "emu_stencil3d")[san]
+    rng = np.random.default_rng(N[2])
+    n1, n2, n3 = N
+    p1, p2, p3 = pads
+    ld = n3 + (n3 & 1)
+    W = (2 * p1 + 1, 2 * p2 + 1, 2 * p3 + 1)
+    S = rng.standard_normal(N + W)
+    S[..., p1, p2, p3] += 30.0                                   # a usable diagonal for the Jacobi epilogues
+    xg = np.zeros((glo + n1 + ghi, n2, ld))
+    xg[..., :n3] = rng.standard_normal((glo + n1 + ghi, n2, n3))
+    b = np.zeros((n1, n2, ld))
+    b[..., :n3] = rng.standard_normal(N)
+    xpad = np.zeros((n1 + 2 * p1, n2 + 2 * p2, n3 + 2 * p3))
+    xpad[p1 - glo:p1 + n1 + ghi, p2:p2 + n2, p3:p3 + n3] = xg[..., :n3]
+    Ax = np.zeros(N)
+    for k1 in range(W[0]):
+        for k2 in range(W[1]):
+            for k3 in range(W[2]):
+                Ax += S[..., k1, k2, k3] * xpad[k1:k1 + n1, k2:k2 + n2, k3:k3 + n3]
+    x = xg[glo:glo + n1, :, :n3]
+    dg = S[..., p1, p2, p3]
+    om = 0.7
+    want = {0: (Ax, np.sum(x * Ax)), 1: (b[..., :n3] - Ax, np.sum((b[..., :n3] - Ax) ** 2)),
+            2: (x + om * (b[..., :n3] - Ax) / dg, np.sum((om * (b[..., :n3] - Ax) / dg) ** 2)),
+            3: (om * (b[..., :n3] - Ax) / dg, np.sum((om * (b[..., :n3] - Ax) / dg) ** 2)),
+            4: (b[..., :n3] + om * Ax, np.sum((om * Ax) ** 2))}
+    for epi, (y_ref, dot_ref) in want.items():
+        dot, y = _stencil3d(exe, tmp_path, 0, N, pads, ld, epi=epi, has_dot=1, glo=glo, ghi=ghi, omega=om,
+                            arrays=[xg, b, S], has_b=1)
+        assert rel(y[..., :n3], y_ref) < 1e-14 and abs(dot - dot_ref) <= 1e-13 * abs(dot_ref)
+        assert not y[..., n3:].any()                             # the pad column is never written
+    _, y = _stencil3d(exe, tmp_path, 0, N, pads, ld, epi=0, has_dot=0, glo=glo, ghi=ghi, arrays=[xg, S])
+    assert rel(y[..., :n3], Ax) < 1e-14
+    # two-colour half sweeps: both colours, both offsets
+    d = np.zeros((n1, n2, ld))
+    d[..., :n3] = rng.standard_normal(N)
+    i1, i2, i3 = np.meshgrid(np.arange(n1), np.arange(n2), np.arange(n3), indexing="ij")
+    for off in (0, 1):
+        for colour in (0, 1):
+            _, xn = _stencil3d(exe, tmp_path, 1, N, pads, ld, off=off, colour=colour, arrays=[b, d])
+            mask = ((i1 + i2 + i3 + off) & 1) == colour
+            assert np.array_equal(xn[..., :n3], np.where(mask, b[..., :n3] + d[..., :n3], b[..., :n3]))
 
 
 @pytest.mark.parametrize("san", ["asan", "tsan"])
