@@ -4,6 +4,8 @@
 //   op 0  poms_kron_matvec_2d   (round-1 2-D kernel: tiny / misaligned grids; TMA fast path stubbed out)
 //   op 1  poms_cg_update        op 2  poms_p_update      op 3  poms_dot      op 4  poms_axpby
 //   op 5  poms_jacobi_first_2d  op 6  poms_cheb_update
+//   op 7  poms_stencil_matvec_2d  (full 2-D stencil; header: p = p1, form = p2, h[10] / h[11] = ghost rows below / above;
+//         arrays: S (n1 n2 (2p1+1)(2p2+1)), x ((glo + n1 + ghi) * ld), b (n1 * ld, if has_b))
 //   emu_tu0 <in> <out>
 // in:  int32 header (16): {op, n1, n2, ld, p, form, epi, has_b, has_dot, n (flat length), 0...}
 //      fp64 scalars (4): {omega | a, num | b, den, c2}
@@ -66,6 +68,17 @@ int main(int argc, char** argv) {
         else
             rc = poms_jacobi_first_2d(y.get(), b.get(), n1, n2, ld, p, form, m1.get(), k1.get(), m2.get(), k2.get(),
                                       sc[0], has_dot ? &dot : nullptr, ws.get(), nullptr);
+        put(y.get(), total);
+    } else if (op == 7) {       // full 2-D stencil (spl StencilMatrix.dot): p1 = p, p2 = form, ghost rows h[10] / h[11]
+        const int p2 = form, glo = h[10], ghi = h[11];
+        auto S = rd<double>(f, (size_t)n1 * n2 * (2 * p + 1) * (2 * p2 + 1));
+        auto x = rd<double>(f, (size_t)(glo + n1 + ghi) * ld);
+        const size_t total = (size_t)n1 * ld;
+        auto b = rd<double>(f, has_b ? total : 0);
+        std::unique_ptr<double[]> y(new double[total]);
+        for (size_t i = 0; i < total; ++i) y[i] = 0.0;
+        rc = poms_stencil_matvec_2d(x.get() + (size_t)glo * ld, y.get(), has_b ? b.get() : nullptr, S.get(), n1, n2, ld,
+                                    glo, ghi, p, p2, epi, sc[0], has_dot ? &dot : nullptr, ws.get(), nullptr);
         put(y.get(), total);
     } else {
         auto a0 = rd<double>(f, n), a1 = rd<double>(f, n), a2 = rd<double>(f, n), a3 = rd<double>(f, n);

@@ -505,6 +505,44 @@ def test_matvec2d_round1_emulated(tu0_exes, tmp_path, san, p, N):
 
 
 @pytest.mark.parametrize("san", ["asan", "tsan"])
+@pytest.mark.parametrize("N,pads,glo,ghi", [((9, 13), (1, 1), 0, 0), ((12, 301), (3, 2), 0, 0), ((7, 40), (2, 3), 2, 1)])
+def test_full_stencil2d_emulated(tu0_exes, tmp_path, san, N, pads, glo, ghi):
+    """poms_stencil_matvec_2d = spl's StencilMatrix.dot: unequal pads, a last extent that is odd and wider
+    than one block, ghost rows on both sides (the slab form), the four epilogues with their fused reduction."""
+    _core(san, N == (12, 301))
+    EPI, _ = _consts()
+    rng = np.random.default_rng(N[1])
+    n1, n2 = N
+    p1, p2 = pads
+    ld = n2 + (n2 & 1)
+    S = rng.standard_normal(N + (2 * p1 + 1, 2 * p2 + 1))
+    S[..., p1, p2] += 20.0
+    xg = np.zeros((glo + n1 + ghi, ld))
+    xg[:, :n2] = rng.standard_normal((glo + n1 + ghi, n2))
+    b = np.zeros((n1, ld))
+    b[:, :n2] = rng.standard_normal(N)
+    xpad = np.zeros((n1 + 2 * p1, n2 + 2 * p2))
+    xpad[p1 - glo:p1 + n1 + ghi, p2:p2 + n2] = xg[:, :n2]
+    Ax = np.zeros(N)
+    for k1 in range(2 * p1 + 1):
+        for k2 in range(2 * p2 + 1):
+            Ax += S[..., k1, k2] * xpad[k1:k1 + n1, k2:k2 + n2]
+    x, bb, dg, om = xg[glo:glo + n1, :n2], b[:, :n2], S[..., p1, p2], 0.6
+    dr = om * (bb - Ax) / dg
+    want = {"store": (Ax, np.sum(x * Ax)), "resid": (bb - Ax, np.sum((bb - Ax) ** 2)),
+            "jacobi": (x + dr, np.sum(dr ** 2)), "dinv": (dr, np.sum(dr ** 2))}
+    for name, (y_ref, dot_ref) in want.items():
+        dot, (y,) = _call_tu0(tu0_exes[san], tmp_path, [7, n1, n2, ld, p1, p2, EPI[name], 1, 1, 0, glo, ghi], [om],
+                              [S, xg, b], [n1 * ld])
+        y = y.reshape(n1, ld)
+        assert rel(y[:, :n2], y_ref) < 1e-14 and abs(dot - dot_ref) <= 1e-13 * abs(dot_ref)
+        assert not y[:, n2:].any()
+    _, (y,) = _call_tu0(tu0_exes[san], tmp_path, [7, n1, n2, ld, p1, p2, EPI["store"], 0, 0, 0, glo, ghi], [om],
+                        [S, xg], [n1 * ld])
+    assert rel(y.reshape(n1, ld)[:, :n2], Ax) < 1e-14
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
 @pytest.mark.parametrize("n", [1, 31, 1000, 100003])
 def test_cg_vector_algebra_emulated(tu0_exes, tmp_path, san, n):
     """poms_cg_update, poms_p_update, poms_dot, poms_axpby, poms_cheb_update
