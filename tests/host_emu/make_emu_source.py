@@ -217,3 +217,19 @@ def stencil3d_section():
     c = extra.index("// Full (non-separable) 3-D stencil mat-vec")
     c = extra.rfind("\n", 0, extra.rfind("\n", 0, c)) + 1
     return to_host(text[a:b] + extra[c:])
+
+
+def halo_section():
+    """Peer-store halo exchange (poms_extra.cu).  The two inline-PTX wrappers (st.release.sys / ld.acquire.sys)
+    are removed; emu_halo.cpp provides them as sequentially consistent atomics on memory shared between processes."""
+    text = open(os.path.join(CSRC, "poms_extra.cu")).read()
+    a = text.index("// Halo exchange by peer stores.")
+    a = text.rfind("\n", 0, text.rfind("\n", 0, a)) + 1
+    b = text.index("// Dense per-axis contraction on the fp64 tensor cores")
+    b = text.rfind("\n", 0, text.rfind("\n", 0, b)) + 1
+    src = text[a:b]
+    for name in ("st_release_sys", "ld_acquire_sys"):
+        src, n = re.subn(r"__device__ __forceinline__ \w+ %s\(.*?\n}\n" % name, "", src, flags=re.S)
+        assert n == 1, name
+    assert "asm volatile" not in src
+    return to_host(src)

@@ -71,15 +71,18 @@ def emu_builds(tmp_path_factory):
     src, nlaunch = make_emu_source.stencil3d_section()
     assert nlaunch == 2
     (d / "stencil3d_emu.cuh").write_text(src)
+    src, nlaunch = make_emu_source.halo_section()
+    assert nlaunch == 1
+    (d / "halo_emu.cuh").write_text(src)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     procs = {}
     for prog in ("emu_matvec3d_tma", "emu_matvec2d_tma", "emu_transfer", "emu_bandsolve", "emu_matvec3d", "emu_tu0",
-                 "emu_axis_gather", "emu_dmma", "emu_setup", "emu_stencil3d"):
+                 "emu_axis_gather", "emu_dmma", "emu_setup", "emu_stencil3d", "emu_halo"):
         if "_tma" in prog and not os.path.exists(os.path.join(cuda_inc, "cuda.h")):
             continue
         for name, flags in (("asan", ["-fsanitize=address", "-fno-omit-frame-pointer"]),
                             ("tsan", ["-fsanitize=thread"])):
-            if name == "tsan" and ((not FULL and prog not in TSAN_PROGS) or prog == "emu_axis_gather"):
+            if name == "tsan" and ((not FULL and prog not in TSAN_PROGS) or prog in ("emu_axis_gather", "emu_halo")):
                 continue                      # (the gather kernels have no barrier and no shared memory)
             out = str(d / (prog + "_" + name))
             procs[prog, name] = (out, subprocess.Popen(
@@ -1045,6 +1048,42 @@ def test_full_stencil3d_emulated(emu_builds, tmp_path, san, N, pads, glo, ghi):
             _, xn = _stencil3d(exe, tmp_path, 1, N, pads, ld, off=off, colour=colour, arrays=[b, d])
             mask = ((i1 + i2 + i3 + off) & 1) == colour
             assert np.array_equal(xn[..., :n3], np.where(mask, b[..., :n3] + d[..., :n3], b[..., :n3]))
+
+
+# ------------------------------------------------------------------------------------------------
+# Peer-store halo exchange (halo_push_kernel behind poms_halo_exchange_p2p): one PROCESS per rank, the ranks' "IPC"
+# memory is one file mapped shared by all of them, so the ENTER / DATA flag protocol runs between concurrent address
+# spaces that drift apart by random sleeps.  Address sanitizer only (ThreadSanitizer does not see other processes).
+# ------------------------------------------------------------------------------------------------
+def _halo_run(exe, tmp, size, n, exchanges, seed):
+    per = 8 + 2 * n + 8                        # flags | canary | ghost_lo | canary | canary | ghost_hi | canary
+    buf = np.zeros((size, per))
+    buf[:, 8:10] = buf[:, 10 + n:14 + n] = buf[:, 14 + 2 * n:16 + 2 * n] = -7.25e300
+    path = str(tmp / "halo.bin")
+    buf.tofile(path)
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0")
+    procs = [subprocess.Popen([exe, path, str(r), str(size), str(n), str(exchanges), str(seed)],
+                              stderr=subprocess.PIPE, text=True, env=env) for r in range(size)]
+    res = []
+    try:
+        for pr in procs:
+            res.append((pr.wait(timeout=300), pr.stderr.read()[-2000:]))
+    finally:
+        for pr in procs:
+            if pr.poll() is None:
+                pr.kill()                      # (exactly the processes started above)
+    return res
+
+
+@pytest.mark.parametrize("size,n,exchanges", [(2, 64, 4), (3, 5000, 8), (4, 40000, 5), (3, 0, 3)])
+def test_halo_exchange_p2p_emulated(emu_builds, tmp_path, size, n, exchanges):
+    """Every rank's ghost planes hold its neighbours' planes of THE SAME exchange after each call (no rank runs ahead
+    into planes that are still being read, no data missing), sequence numbers advance, the block ticket is reset, the
+    canaries around the ghost planes survive; edge ranks have one neighbour; 1 to 10 blocks; an empty exchange."""
+    _core("asan", size == 3 and n == 5000)
+    exe = _Exes(emu_builds, "emu_halo")["asan"]
+    for rc, err in _halo_run(exe, tmp_path, size, n, exchanges, seed=n + size):
+        assert rc == 0 and not err.strip(), (rc, err)
 
 
 @pytest.mark.parametrize("san", ["asan", "tsan"])
