@@ -4,6 +4,7 @@
 //   op 0  poms_kron_matvec_2d   (round-1 2-D kernel: tiny / misaligned grids; TMA fast path stubbed out)
 //   op 1  poms_cg_update        op 2  poms_p_update      op 3  poms_dot      op 4  poms_axpby
 //   op 5  poms_jacobi_first_2d  op 6  poms_cheb_update
+//   op 8  poms_axpy_dev   op 9  poms_diag_scale   op 10  poms_jacobi_first_3d (n3 = h[10]; bands m1 k1 m2 k2 m3 k3, b)
 //   op 7  poms_stencil_matvec_2d  (full 2-D stencil; header: p = p1, form = p2, h[10] / h[11] = ghost rows below / above;
 //         arrays: S (n1 n2 (2p1+1)(2p2+1)), x ((glo + n1 + ghi) * ld), b (n1 * ld, if has_b))
 //   emu_tu0 <in> <out>
@@ -69,6 +70,18 @@ int main(int argc, char** argv) {
             rc = poms_jacobi_first_2d(y.get(), b.get(), n1, n2, ld, p, form, m1.get(), k1.get(), m2.get(), k2.get(),
                                       sc[0], has_dot ? &dot : nullptr, ws.get(), nullptr);
         put(y.get(), total);
+    } else if (op == 10) {      // first Jacobi sweep in 3-D: extents n1, n2, h[10]; ld = h[3]
+        const int n3 = h[10], W = 2 * p + 1;
+        auto m1 = rd<double>(f, (size_t)n1 * W), k1 = rd<double>(f, (size_t)n1 * W);
+        auto m2 = rd<double>(f, (size_t)n2 * W), k2 = rd<double>(f, (size_t)n2 * W);
+        auto m3 = rd<double>(f, (size_t)n3 * W), k3 = rd<double>(f, (size_t)n3 * W);
+        const size_t total = (size_t)n1 * n2 * ld;
+        auto b = rd<double>(f, total);
+        std::unique_ptr<double[]> y(new double[total]);
+        for (size_t i = 0; i < total; ++i) y[i] = 0.0;
+        rc = poms_jacobi_first_3d(y.get(), b.get(), n1, n2, n3, ld, (int64_t)n2 * ld, p, form, m1.get(), k1.get(), m2.get(),
+                                  k2.get(), m3.get(), k3.get(), sc[0], has_dot ? &dot : nullptr, ws.get(), nullptr);
+        put(y.get(), total);
     } else if (op == 7) {       // full 2-D stencil (spl StencilMatrix.dot): p1 = p, p2 = form, ghost rows h[10] / h[11]
         const int p2 = form, glo = h[10], ghi = h[11];
         auto S = rd<double>(f, (size_t)n1 * n2 * (2 * p + 1) * (2 * p2 + 1));
@@ -94,6 +107,12 @@ int main(int argc, char** argv) {
             rc = poms_dot(a0.get(), a1.get(), (int64_t)n, &dot, ws.get(), nullptr);
         } else if (op == 4) {   // z = a x + b y
             rc = poms_axpby(a0.get(), sc[0], a1.get(), sc[1], a2.get(), (int64_t)n, nullptr);
+            put(a0.get(), n);
+        } else if (op == 8) {   // y += sign * (num / den) * x
+            rc = poms_axpy_dev(a0.get(), a1.get(), (int64_t)n, &sc[1], &sc[2], sc[0], nullptr);
+            put(a0.get(), n);
+        } else if (op == 9) {   // x = omega * b / d, fused sum of squares
+            rc = poms_diag_scale(a0.get(), a1.get(), a2.get(), (int64_t)n, sc[0], has_dot ? &dot : nullptr, ws.get(), nullptr);
             put(a0.get(), n);
         } else if (op == 6) {   // d = c1 d + c2 z ; x += d
             rc = poms_cheb_update(a0.get(), a1.get(), a2.get(), sc[0], sc[3], (int64_t)n, nullptr);

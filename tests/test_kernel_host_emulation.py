@@ -508,6 +508,42 @@ def test_matvec2d_round1_emulated(tu0_exes, tmp_path, san, p, N):
 
 
 @pytest.mark.parametrize("san", ["asan", "tsan"])
+def test_remaining_vector_kernels_emulated(tu0_exes, tmp_path, san):
+    """poms_axpy_dev, poms_diag_scale (with and without the fused sum) and the 3-D form of poms_jacobi_first (several
+    planes per block column: gridDim.z < n1), sum and single forms."""
+    _core(san, False)
+    exe = tu0_exes[san]
+    _, FORM = _consts()
+    rng = np.random.default_rng(8)
+    for n in (1, 777, 5001):
+        x, y, d = rng.standard_normal(n), rng.standard_normal(n), 1.0 + rng.random(n)
+        z = np.zeros(n)
+        _, (o,) = _call_tu0(exe, tmp_path, [8, 0, 0, 0, 0, 0, 0, 0, 0, n], [-1.0, 3.0, 7.0], [y, x, z, z], [n])
+        assert rel(o, y - 3.0 / 7.0 * x) < 1e-15
+        dot, (o,) = _call_tu0(exe, tmp_path, [9, 0, 0, 0, 0, 0, 0, 0, 1, n], [0.8], [z, x, d, z], [n])
+        assert rel(o, 0.8 * x / d) < 1e-15 and abs(dot - np.sum((0.8 * x / d) ** 2)) <= 1e-13 * dot
+        _, (o,) = _call_tu0(exe, tmp_path, [9, 0, 0, 0, 0, 0, 0, 0, 0, n], [0.8], [z, x, d, z], [n])
+        assert rel(o, 0.8 * x / d) < 1e-15
+    for p, N in [(2, (70, 5, 9)), (3, (9, 8, 300))]:
+        n1, n2, n3 = N
+        ld = n3 + (n3 & 1)
+        bands = [rng.standard_normal((n, 2 * p + 1)) + 5.0 * (np.arange(2 * p + 1) == p) for n in N for _ in (0, 1)]
+        m1, k1, m2, k2, m3, k3 = bands
+        b = np.zeros((n1, n2, ld))
+        b[..., :n3] = rng.standard_normal(N)
+        M = [m[:, p] for m in (m1, m2, m3)]
+        K = [k[:, p] for k in (k1, k2, k3)]
+        o3 = lambda a, bb, c: a[:, None, None] * bb[None, :, None] * c[None, None, :]
+        diag = {"single": o3(*M), "sum": o3(K[0], M[1], M[2]) + o3(M[0], K[1], M[2]) + o3(M[0], M[1], K[2])}
+        for form in ("sum", "single"):
+            dot, (o,) = _call_tu0(exe, tmp_path, [10, n1, n2, ld, p, FORM[form], 0, 1, 1, 0, n3], [0.7],
+                                  bands + [b], [n1 * n2 * ld])
+            o = o.reshape(n1, n2, ld)
+            ref = 0.7 * b[..., :n3] / diag[form]
+            assert rel(o[..., :n3], ref) < 1e-14 and abs(dot - np.sum(ref ** 2)) <= 1e-13 * dot and not o[..., n3:].any()
+
+
+@pytest.mark.parametrize("san", ["asan", "tsan"])
 @pytest.mark.parametrize("N,pads,glo,ghi", [((9, 13), (1, 1), 0, 0), ((12, 301), (3, 2), 0, 0), ((7, 40), (2, 3), 2, 1)])
 def test_full_stencil2d_emulated(tu0_exes, tmp_path, san, N, pads, glo, ghi):
     """poms_stencil_matvec_2d = spl's StencilMatrix.dot: unequal pads, a last extent that is odd and wider
